@@ -1,0 +1,162 @@
+/* svi_ls.h -- C ABI of the B200 link-sampling engine (libsvi_ls.so).
+ *
+ * This is the drop-in boundary for ONE path of premgopalan/svinet: the body of
+ * LinkSampling::infer's while(1) loop (reference src/linksampling.cc:571-789) and the
+ * held-out likelihood it evaluates every report (src/linksampling.cc:966-1050,
+ * src/linksampling.hh:259-292).  The reference has no FFI; its seam is the C++ class
+ * `LinkSampling` used at src/main.cc:337-341.  A replacement `LinkSampling` keeps the
+ * reference's host responsibilities (Env, Network, held-out draw, init_gamma2, file
+ * writers, stop state machine) and drives the device through the calls below; see
+ * INTEGRATION.md for the binding a maintainer adds on the reference side.
+ *
+ * Conventions: plain C types; caller-owned HOST buffers unless a name says `_dev`;
+ * every call returns 0 on success or a negative svi_status, with a message available
+ * from svi_ls_last_error().  A handle is bound to one CUDA device and one stream and
+ * must be driven by one host thread at a time.  All arithmetic is FP64 (the reference
+ * is FP64 throughout).
+ */
+#ifndef SVI_LS_H
+#define SVI_LS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVI_LS_ABI_VERSION 1
+
+typedef enum svi_status {
+  SVI_OK = 0,
+  SVI_ERR_INVALID = -1,   /* bad argument                                   */
+  SVI_ERR_CUDA = -2,      /* a CUDA runtime call or kernel failed           */
+  SVI_ERR_NOMEM = -3,     /* host or device allocation failed               */
+  SVI_ERR_UNSUPPORTED = -4/* e.g. K larger than the register-tiled kernels  */
+} svi_status;
+
+typedef struct svi_ls svi_ls; /* opaque */
+
+/* Static description of one inference problem.
+ * Replaces the constructor state of LinkSampling (src/linksampling.cc:5-33) that the
+ * sweep reads: _n, _k, env.alpha (src/env.hh:344), env.eta0/eta1 (src/network.cc:233-250),
+ * _network.ones() (numerator of the annealing rescale, src/linksampling.cc:542). */
+typedef struct svi_ls_config {
+  uint32_t n;          /* inference nodes (env.n after src/main.cc:291)                    */
+  uint32_t k;          /* communities                                                      */
+  uint64_t nlinks;     /* training links, one (p<q) pair each                              */
+  double   alpha;      /* Dirichlet prior, 1/k in the reference                            */
+  double   eta0, eta1; /* Beta prior                                                       */
+  uint32_t ones;       /* all links of the network incl. held-out ones                     */
+  int32_t  device;     /* CUDA ordinal; -1 = the calling thread's current device           */
+  uint32_t seg_len;    /* neighbours per work segment; 0 = choose automatically            */
+  /* Node-block shard owned by this handle (multi-GPU).  A single
+   * GPU run uses node_begin = 0, node_end = n.  The handle sweeps only half-edges whose
+   * source node is in [node_begin, node_end) and refreshes only those rows; the caller
+   * exchanges the row blocks and the K-vectors between phases (see svi_ls_phase_*). */
+  uint32_t node_begin, node_end;
+} svi_ls_config;
+
+/* Build the device-side problem: CSR adjacency over the training links, work segments,
+ * state matrices.  Replaces LinkSampling::assign_training_links' product `_links` /
+ * `_training_links` (src/linksampling.cc:493-523).
+ *   links : [2*nlinks] uint32, (p,q) with p<q, any order (the reference order is not
+ *           needed: the device path is order-independent by construction)
+ *   tl    : [n] the reference's _training_links (= 2 x training degree),
+ *           or NULL to derive it from `links`. */
+int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double *tl, svi_ls **out);
+void svi_ls_destroy(svi_ls *h);
+
+/* Launch on the caller's stream (a cudaStream_t passed as void*; NULL = legacy default). */
+int svi_ls_set_stream(svi_ls *h, void *cuda_stream);
+int svi_ls_sync(svi_ls *h);
+
+/* Upload gamma [n*k row-major] and lambda [k*2] and derive the expectations the sweep
+ * reads.  Replaces init_gamma2/init_lambda/load_model hand-off + set_dir_exp at
+ * src/linksampling.cc:110-124 and :561-563.  Does not touch `converged`. */
+int svi_ls_set_state(svi_ls *h, const double *gamma, const double *lambda);
+/* Download gamma [n*k] / lambda [k*2] (either may be NULL).  For save_model /
+ * write_groups / SIGTERM dumps (src/linksampling.cc:793-837, :1453-1476). */
+int svi_ls_get_state(svi_ls *h, double *gamma, double *lambda);
+
+/* _converged (src/linksampling.cc:456-475): 0 or community+1 per node.  create() zeroes it
+ * (infer() does, :559); set is for resuming from a known state. */
+int svi_ls_set_converged(svi_ls *h, const uint32_t *converged);
+int svi_ls_get_converged(svi_ls *h, uint32_t *converged, uint32_t *active_comms);
+
+/* One full iteration on the device == the loop body src/linksampling.cc:584-761:
+ * phi sweep (dense :685-701, converged shortcut :619-631, active-set form :634-681 when
+ * iter > 1000), compute_mean_indicators (:526-545), s3 sweep (:731-746), lambda finish
+ * (:748-755), set_dir_exp x2 (:757-759), prune (:761).
+ *   iter       : the reference's _iter (only its relation to 1000 matters)
+ *   annealing  : _annealing_phase (:541)
+ *   write_comm : when non-zero the link-community tally (:704-717) is rebuilt; read it
+ *                back with svi_ls_get_membership.
+ * Asynchronous on the handle's stream. */
+int svi_ls_step(svi_ls *h, uint32_t iter, int annealing, int write_comm);
+
+/* Link-community membership of the last write_comm sweep: bit c of word
+ * bits[p*words + c/32] is set iff node p is an endpoint of a full-phi link whose arg-max
+ * community is c (replaces _fmap/_communities, src/linksampling.cc:668-681,704-717, with
+ * link_thresh = lt_min_deg = 0).  words = (k+31)/32. */
+int svi_ls_get_membership(svi_ls *h, uint32_t *bits);
+
+/* Held-out log-likelihood of `npairs` node pairs under the current gamma/lambda:
+ * LinkSampling::edge_likelihood (src/linksampling.hh:259-292) incl. the 1e-30 floor;
+ * y[i] = 1 for a link.  The caller sums in its own order (validation_likelihood,
+ * src/linksampling.cc:966-1002). */
+int svi_ls_heldout(svi_ls *h, uint64_t npairs, const uint32_t *p, const uint32_t *q,
+                   const uint8_t *y, double epsilon, double *loglik);
+
+/* The four K-vectors of the last sweep (_sum,_s1,_s2,_s3; src/linksampling.hh:157); any
+ * pointer may be NULL.  Diagnostics and parity tests. */
+int svi_ls_get_kvectors(svi_ls *h, double *sum, double *s1, double *s2, double *s3);
+
+/* ---- phase-level entry points (multi-GPU drivers) -------------
+ * svi_ls_step == phase_phi; phase_node; phase_s3; phase_finish run back to back.  A
+ * sharded driver interleaves its collectives on the buffers returned by
+ * svi_ls_device_buffer between the phases:
+ *   phase_phi   : phi sweep over the shard's half-edges            -> per-segment partial rows
+ *   phase_node  : mean indicators for the shard's rows             -> SVI_BUF_MPHI rows, local
+ *                 column sums in SVI_BUF_KVEC (sum,s1,s2)            [all-reduce sum,s1,s2;
+ *                                                                     all-gather mphi rows]
+ *   phase_s3    : s3 over the shard's (p<q) half-edges             -> SVI_BUF_KVEC (s3) [all-reduce]
+ *   phase_finish: lambda, Elogbeta, gamma rescale, Elogpi, prune   -> SVI_BUF_EXPPI rows,
+ *                 SVI_BUF_CONVERGED                                  [all-gather both] */
+int svi_ls_phase_phi(svi_ls *h, uint32_t iter, int write_comm);
+int svi_ls_phase_node(svi_ls *h);
+int svi_ls_phase_s3(svi_ls *h);
+int svi_ls_phase_finish(svi_ls *h, int annealing);
+
+typedef enum svi_buffer {
+  SVI_BUF_EXPPI = 0,     /* double [n * ld]  exp(Elogpi - rowmax), rows padded to ld  */
+  SVI_BUF_MPHI = 1,      /* double [n * ld]                                           */
+  SVI_BUF_GAMMA = 2,     /* double [n * ld]                                           */
+  SVI_BUF_KVEC = 3,      /* double [4 * ld]: sum, s1, s2, s3 (local to the shard)     */
+  SVI_BUF_CONVERGED = 4, /* uint32 [n]                                                */
+  SVI_BUF_LAMBDA = 5,    /* double [k * 2]                                            */
+  SVI_BUF_ACTIVE = 6,    /* uint32 [n]  active_comms (read by the iter > 1000 branch) */
+  SVI_BUF_ACTIVE_BITS = 7,/* uint32 [n * words] active-community mask, same branch    */
+  SVI_BUF_MEMBER_BITS = 8/* uint32 [n * words] link-community membership              */
+} svi_buffer;
+/* Device pointer + leading dimension (in elements) of an exchange buffer. */
+int svi_ls_device_buffer(svi_ls *h, svi_buffer which, void **dev_ptr, uint64_t *ld);
+
+/* Work counters of the problem: half-edges swept by phase_phi / phase_s3, segments. */
+typedef struct svi_ls_info {
+  uint64_t half_edges_phi, half_edges_s3, segments_phi, segments_s3;
+  uint32_t ld;            /* padded row length (elements)                              */
+  uint32_t seg_len;
+  uint32_t lanes, vec;    /* kernel tiling actually selected for this K                */
+  uint64_t device_bytes;  /* HBM allocated by the handle                               */
+  uint32_t kernels_per_step;
+} svi_ls_info;
+int svi_ls_get_info(svi_ls *h, svi_ls_info *info);
+
+const char *svi_ls_last_error(void);
+int svi_ls_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVI_LS_H */

@@ -1,0 +1,599 @@
+// svi_ls.cu -- C ABI (include/svi_ls.h) over the sm_100a kernels in svi_ls_kernels.cuh.
+//
+// Host side of the device path only: CSR / segment construction, buffer management, kernel
+// dispatch by K, stream plumbing.  No CPU compute fallback exists: every entry point that
+// needs the GPU fails with SVI_ERR_CUDA when there is none.
+#include "../../include/svi_ls.h"
+#include "svi_ls_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(SVI_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+using svi::Params;
+
+// launchers for one (G, V, LOGDOM) tiling
+struct Ops {
+  void (*phi)(const Params &, cudaStream_t, bool sparse, bool comm);
+  void (*node)(const Params &, cudaStream_t, uint32_t blocks);
+  void (*s3)(const Params &, cudaStream_t, uint32_t blocks);
+  void (*lambda)(const Params &, cudaStream_t, int annealing, int update);
+  void (*refresh)(const Params &, cudaStream_t, bool from_gacc);
+  void (*heldout)(const Params &, cudaStream_t, uint64_t, const uint32_t *, const uint32_t *, const uint8_t *,
+                  double, double *);
+  int (*max_blocks_node)(int sms);
+  int (*max_blocks_s3)(int sms);
+  int lanes, vec, logdom;
+};
+
+constexpr int kThreads = 256;
+
+template <int G, int V, bool L>
+struct Tile {
+  static constexpr int CAP = 2 * G * V;
+  static constexpr size_t kSmem = (size_t)(kThreads / G) * CAP * sizeof(double);
+
+  static void phi(const Params &P, cudaStream_t st, bool sparse, bool comm) {
+    if (!P.nseg) return;
+    const uint32_t blocks = (uint32_t)(((uint64_t)P.nseg * G + kThreads - 1) / kThreads);
+    if (sparse && comm) svi::k_phi<G, V, L, true, true><<<blocks, kThreads, 0, st>>>(P);
+    else if (sparse) svi::k_phi<G, V, L, true, false><<<blocks, kThreads, 0, st>>>(P);
+    else if (comm) svi::k_phi<G, V, L, false, true><<<blocks, kThreads, 0, st>>>(P);
+    else svi::k_phi<G, V, L, false, false><<<blocks, kThreads, 0, st>>>(P);
+  }
+  static void node(const Params &P, cudaStream_t st, uint32_t blocks) {
+    svi::k_node<G, V><<<blocks, kThreads, kSmem, st>>>(P);
+  }
+  static void s3(const Params &P, cudaStream_t st, uint32_t blocks) {
+    svi::k_s3<G, V><<<blocks, kThreads, kSmem, st>>>(P);
+  }
+  static void lambda(const Params &P, cudaStream_t st, int annealing, int update) {
+    svi::k_lambda<L><<<1, kThreads, 0, st>>>(P, annealing, update);
+  }
+  static void refresh(const Params &P, cudaStream_t st, bool from_gacc) {
+    const uint32_t rows = P.node_end - P.node_begin;
+    if (!rows) return;
+    const uint32_t blocks = (uint32_t)(((uint64_t)rows * G + kThreads - 1) / kThreads);
+    if (from_gacc) svi::k_refresh<G, V, L, true><<<blocks, kThreads, 0, st>>>(P);
+    else svi::k_refresh<G, V, L, false><<<blocks, kThreads, 0, st>>>(P);
+  }
+  static void heldout(const Params &P, cudaStream_t st, uint64_t np, const uint32_t *p, const uint32_t *q,
+                      const uint8_t *y, double eps, double *out) {
+    if (!np) return;
+    const uint32_t blocks = (uint32_t)((np * G + kThreads - 1) / kThreads);
+    svi::k_heldout<G, V><<<blocks, kThreads, 0, st>>>(P, np, p, q, y, eps, out);
+  }
+  static int occ(const void *fn, int sms) {
+    int per_sm = 0;
+    if (kSmem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, kSmem) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    return per_sm * sms;
+  }
+  static int max_blocks_node(int sms) { return occ((const void *)svi::k_node<G, V>, sms); }
+  static int max_blocks_s3(int sms) { return occ((const void *)svi::k_s3<G, V>, sms); }
+  static Ops ops() {
+    return Ops{phi, node, s3, lambda, refresh, heldout, max_blocks_node, max_blocks_s3, G, V, L ? 1 : 0};
+  }
+};
+
+// K -> tiling.  Factorised (exp-domain) rows up to K = 256; log-domain above (underflow, see .cuh)
+bool pick_ops(uint32_t k, Ops *o) {
+  if (k == 0) return false;
+  if (k <= 4) *o = Tile<2, 1, false>::ops();
+  else if (k <= 8) *o = Tile<4, 1, false>::ops();
+  else if (k <= 16) *o = Tile<8, 1, false>::ops();
+  else if (k <= 32) *o = Tile<16, 1, false>::ops();
+  else if (k <= 64) *o = Tile<32, 1, false>::ops();
+  else if (k <= 128) *o = Tile<32, 2, false>::ops();
+  else if (k <= 192) *o = Tile<32, 3, false>::ops();
+  else if (k <= 256) *o = Tile<32, 4, false>::ops();
+  else if (k <= 384) *o = Tile<32, 6, true>::ops();
+  else if (k <= 512) *o = Tile<32, 8, true>::ops();
+  else if (k <= 768) *o = Tile<32, 12, true>::ops();
+  else if (k <= 1024) *o = Tile<32, 16, true>::ops();
+  else return false;
+  return true;
+}
+
+template <class T>
+cudaError_t dalloc(T **p, size_t count, uint64_t *total) {
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  cudaError_t e = cudaMalloc((void **)p, bytes);
+  if (e == cudaSuccess) {
+    *total += bytes;
+    e = cudaMemset(*p, 0, bytes);
+  }
+  return e;
+}
+
+}  // namespace
+
+struct svi_ls {
+  svi_ls_config cfg{};
+  int device = 0, sms = 0;
+  cudaStream_t stream = nullptr;
+  Ops ops{};
+  Params P{};
+  uint32_t nlocal = 0, blocks_node = 0, blocks_s3 = 0, kpart_blocks = 0;
+  uint64_t he_phi = 0, he_s3 = 0, device_bytes = 0;
+  uint32_t seg_len = 0;
+  // owned device memory
+  uint32_t *d_col = nullptr, *d_seg_node = nullptr, *d_seg_beg = nullptr, *d_seg_cnt = nullptr;
+  uint32_t *d_node_seg_off = nullptr, *d_seg3_node = nullptr, *d_seg3_beg = nullptr, *d_seg3_cnt = nullptr;
+  double *d_tl = nullptr, *d_b = nullptr, *d_mphi = nullptr, *d_gamma = nullptr, *d_gacc = nullptr;
+  double *d_part = nullptr, *d_kvec = nullptr, *d_kpart = nullptr, *d_lambda = nullptr, *d_eb = nullptr;
+  double *d_scale = nullptr, *d_stage = nullptr;
+  uint32_t *d_conv = nullptr, *d_active = nullptr, *d_abits = nullptr, *d_mbits = nullptr;
+  size_t stage_elems = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+void free_all(svi_ls *h) {
+  void *ptrs[] = {h->d_col, h->d_seg_node, h->d_seg_beg, h->d_seg_cnt, h->d_node_seg_off, h->d_seg3_node,
+                  h->d_seg3_beg, h->d_seg3_cnt, h->d_tl, h->d_b, h->d_mphi, h->d_gamma, h->d_gacc, h->d_part,
+                  h->d_kvec, h->d_kpart, h->d_lambda, h->d_eb, h->d_scale, h->d_stage, h->d_conv, h->d_active,
+                  h->d_abits, h->d_mbits};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+}
+
+int ensure_stage(svi_ls *h, size_t elems) {
+  if (h->stage_elems >= elems) return SVI_OK;
+  if (h->d_stage) cudaFree(h->d_stage);
+  h->d_stage = nullptr;
+  h->stage_elems = 0;
+  CK(cudaMalloc((void **)&h->d_stage, std::max<size_t>(elems, 1) * sizeof(double)));
+  h->stage_elems = elems;
+  return SVI_OK;
+}
+
+// balanced split of `deg` neighbours into chunks of at most seg_len
+inline void push_segments(uint32_t node, uint32_t beg, uint32_t deg, uint32_t seg_len, std::vector<uint32_t> &sn,
+                          std::vector<uint32_t> &sb, std::vector<uint32_t> &sc) {
+  if (!deg) return;
+  const uint32_t nch = (deg + seg_len - 1) / seg_len;
+  const uint32_t base = deg / nch, extra = deg % nch;
+  uint32_t at = beg;
+  for (uint32_t c = 0; c < nch; ++c) {
+    const uint32_t len = base + (c < extra ? 1u : 0u);
+    sn.push_back(node);
+    sb.push_back(at);
+    sc.push_back(len);
+    at += len;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *svi_ls_last_error(void) { return g_err; }
+int svi_ls_abi_version(void) { return SVI_LS_ABI_VERSION; }
+
+int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double *tl, svi_ls **out) {
+  if (!cfg || !out || (!links && cfg->nlinks)) return fail(SVI_ERR_INVALID, "svi_ls_create: null argument");
+  *out = nullptr;
+  if (cfg->n == 0 || cfg->k == 0) return fail(SVI_ERR_INVALID, "svi_ls_create: n and k must be positive");
+  if (cfg->node_begin > cfg->node_end || cfg->node_end > cfg->n)
+    return fail(SVI_ERR_INVALID, "svi_ls_create: bad shard [%u,%u) for n=%u", cfg->node_begin, cfg->node_end, cfg->n);
+  Ops ops;
+  if (!pick_ops(cfg->k, &ops)) return fail(SVI_ERR_UNSUPPORTED, "svi_ls_create: k=%u not supported (max 1024)", cfg->k);
+
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return fail(SVI_ERR_CUDA, "svi_ls_create: no CUDA device");
+  int dev = cfg->device;
+  if (dev < 0) CK(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(SVI_ERR_INVALID, "svi_ls_create: device %d of %d", dev, ndev);
+
+  svi_ls *h = new (std::nothrow) svi_ls();
+  if (!h) return fail(SVI_ERR_NOMEM, "svi_ls_create: host allocation failed");
+  h->cfg = *cfg;
+  h->device = dev;
+  h->ops = ops;
+  DeviceGuard guard(dev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    delete h;
+    return fail(SVI_ERR_CUDA, "svi_ls_create: cudaGetDeviceProperties failed");
+  }
+  h->sms = prop.multiProcessorCount;
+
+  const uint32_t n = cfg->n, k = cfg->k, nb = cfg->node_begin, ne = cfg->node_end;
+  const uint32_t nlocal = ne - nb, ld = (k + 3u) & ~3u, words = (k + 31u) / 32u;
+  h->nlocal = nlocal;
+
+  // ---- CSR of the shard's half-edges; lower neighbours first, upper (q > p) last ----
+  std::vector<uint32_t> deg_lo(nlocal, 0), deg_up(nlocal, 0);
+  std::vector<double> tl_host(n, 0.0);
+  for (uint64_t e = 0; e < cfg->nlinks; ++e) {
+    const uint32_t p = links[2 * e], q = links[2 * e + 1];
+    if (p >= n || q >= n || p == q) {
+      delete h;
+      return fail(SVI_ERR_INVALID, "svi_ls_create: link %llu = (%u,%u) out of range", (unsigned long long)e, p, q);
+    }
+    const uint32_t lo = std::min(p, q), hi = std::max(p, q);
+    if (lo >= nb && lo < ne) deg_up[lo - nb]++;
+    if (hi >= nb && hi < ne) deg_lo[hi - nb]++;
+    tl_host[lo] += 2.0;   // Q3: both adjacency directions count each link for both endpoints
+    tl_host[hi] += 2.0;
+  }
+  if (tl) std::copy(tl, tl + n, tl_host.begin());
+  std::vector<uint64_t> off(nlocal + 1, 0);
+  for (uint32_t v = 0; v < nlocal; ++v) off[v + 1] = off[v] + deg_lo[v] + deg_up[v];
+  const uint64_t he = off[nlocal];
+  if (he > 0xffffffffull) {
+    delete h;
+    return fail(SVI_ERR_UNSUPPORTED, "svi_ls_create: %llu half-edges exceed the 32-bit CSR of one shard",
+                (unsigned long long)he);
+  }
+  std::vector<uint32_t> col(std::max<uint64_t>(he, 1));
+  {
+    std::vector<uint64_t> cur_lo(nlocal), cur_up(nlocal);
+    for (uint32_t v = 0; v < nlocal; ++v) {
+      cur_lo[v] = off[v];
+      cur_up[v] = off[v] + deg_lo[v];
+    }
+    for (uint64_t e = 0; e < cfg->nlinks; ++e) {
+      const uint32_t p = links[2 * e], q = links[2 * e + 1];
+      const uint32_t lo = std::min(p, q), hi = std::max(p, q);
+      if (lo >= nb && lo < ne) col[cur_up[lo - nb]++] = hi;
+      if (hi >= nb && hi < ne) col[cur_lo[hi - nb]++] = lo;
+    }
+  }
+  uint64_t he3 = 0;
+  for (uint32_t v = 0; v < nlocal; ++v) he3 += deg_up[v];
+  h->he_phi = he;
+  h->he_s3 = he3;
+
+  // ---- work segments ----
+  uint32_t seg_len = cfg->seg_len;
+  if (!seg_len) {
+    // enough segments to fill the machine several times over, long enough to amortise the
+    // per-segment row load/store
+    const uint64_t target = (uint64_t)h->sms * 64 * (32 / ops.lanes > 0 ? 32 / ops.lanes : 1);
+    seg_len = 256;
+    while (seg_len > 16 && he / seg_len < target) seg_len >>= 1;
+  }
+  h->seg_len = seg_len;
+  std::vector<uint32_t> sn, sb, sc, s3n, s3b, s3c, nso(nlocal + 1, 0);
+  sn.reserve(he / seg_len + nlocal);
+  sb.reserve(he / seg_len + nlocal);
+  sc.reserve(he / seg_len + nlocal);
+  for (uint32_t v = 0; v < nlocal; ++v) {
+    push_segments(nb + v, (uint32_t)off[v], deg_lo[v] + deg_up[v], seg_len, sn, sb, sc);
+    nso[v + 1] = (uint32_t)sn.size();
+    push_segments(nb + v, (uint32_t)(off[v] + deg_lo[v]), deg_up[v], seg_len, s3n, s3b, s3c);
+  }
+  const uint32_t nseg = (uint32_t)sn.size(), nseg3 = (uint32_t)s3n.size();
+
+  // ---- device memory ----
+  uint64_t &tot = h->device_bytes;
+  const size_t nld = (size_t)n * ld;
+  h->blocks_node = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ops.max_blocks_node(h->sms),
+                                                                   ((int64_t)nlocal * ops.lanes + kThreads - 1) / kThreads));
+  h->blocks_s3 = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ops.max_blocks_s3(h->sms),
+                                                                 ((int64_t)nseg3 * ops.lanes + kThreads - 1) / kThreads));
+  h->kpart_blocks = std::max(h->blocks_node, h->blocks_s3);
+  const size_t cap = 2 * (size_t)ops.lanes * ops.vec;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  A(dalloc(&h->d_col, col.size(), &tot));
+  A(dalloc(&h->d_seg_node, nseg, &tot));
+  A(dalloc(&h->d_seg_beg, nseg, &tot));
+  A(dalloc(&h->d_seg_cnt, nseg, &tot));
+  A(dalloc(&h->d_node_seg_off, nlocal + 1, &tot));
+  A(dalloc(&h->d_seg3_node, nseg3, &tot));
+  A(dalloc(&h->d_seg3_beg, nseg3, &tot));
+  A(dalloc(&h->d_seg3_cnt, nseg3, &tot));
+  A(dalloc(&h->d_tl, n, &tot));
+  A(dalloc(&h->d_b, nld, &tot));
+  A(dalloc(&h->d_mphi, nld, &tot));
+  A(dalloc(&h->d_gamma, nld, &tot));
+  A(dalloc(&h->d_gacc, nld, &tot));
+  A(dalloc(&h->d_part, (size_t)nseg * ld, &tot));
+  A(dalloc(&h->d_kvec, 4 * (size_t)ld, &tot));
+  A(dalloc(&h->d_kpart, (size_t)h->kpart_blocks * 3 * cap, &tot));
+  A(dalloc(&h->d_lambda, 2 * (size_t)k, &tot));
+  A(dalloc(&h->d_eb, ld, &tot));
+  A(dalloc(&h->d_scale, ld, &tot));
+  A(dalloc(&h->d_conv, n, &tot));
+  A(dalloc(&h->d_active, n, &tot));
+  A(dalloc(&h->d_abits, (size_t)n * words, &tot));
+  A(dalloc(&h->d_mbits, (size_t)n * words, &tot));
+  auto H2D = [&](void *d, const void *s, size_t bytes) {
+    if (bytes) A(cudaMemcpy(d, s, bytes, cudaMemcpyHostToDevice));
+  };
+  if (e == cudaSuccess) {
+    H2D(h->d_col, col.data(), he * sizeof(uint32_t));
+    H2D(h->d_seg_node, sn.data(), nseg * sizeof(uint32_t));
+    H2D(h->d_seg_beg, sb.data(), nseg * sizeof(uint32_t));
+    H2D(h->d_seg_cnt, sc.data(), nseg * sizeof(uint32_t));
+    H2D(h->d_node_seg_off, nso.data(), (nlocal + 1) * sizeof(uint32_t));
+    H2D(h->d_seg3_node, s3n.data(), nseg3 * sizeof(uint32_t));
+    H2D(h->d_seg3_beg, s3b.data(), nseg3 * sizeof(uint32_t));
+    H2D(h->d_seg3_cnt, s3c.data(), nseg3 * sizeof(uint32_t));
+    H2D(h->d_tl, tl_host.data(), n * sizeof(double));
+  }
+  if (e != cudaSuccess) {
+    const int rc = fail(e == cudaErrorMemoryAllocation ? SVI_ERR_NOMEM : SVI_ERR_CUDA, "svi_ls_create: %s",
+                        cudaGetErrorString(e));
+    free_all(h);
+    delete h;
+    return rc;
+  }
+
+  Params &P = h->P;
+  P.n = n; P.k = k; P.ld = ld; P.words = words;
+  P.node_begin = nb; P.node_end = ne;
+  P.alpha = cfg->alpha; P.eta0 = cfg->eta0; P.eta1 = cfg->eta1; P.ones_d = (double)cfg->ones;
+  P.k_div10 = k / 10;
+  P.col = h->d_col;
+  P.seg_node = h->d_seg_node; P.seg_beg = h->d_seg_beg; P.seg_cnt = h->d_seg_cnt; P.nseg = nseg;
+  P.node_seg_off = h->d_node_seg_off;
+  P.seg3_node = h->d_seg3_node; P.seg3_beg = h->d_seg3_beg; P.seg3_cnt = h->d_seg3_cnt; P.nseg3 = nseg3;
+  P.tl = h->d_tl;
+  P.b = h->d_b; P.mphi = h->d_mphi; P.gamma = h->d_gamma; P.gacc = h->d_gacc; P.part = h->d_part;
+  P.kvec = h->d_kvec; P.kpart = h->d_kpart; P.lambda = h->d_lambda; P.eb = h->d_eb; P.scale = h->d_scale;
+  P.conv = h->d_conv; P.active = h->d_active; P.abits = h->d_abits; P.mbits = h->d_mbits;
+  *out = h;
+  return SVI_OK;
+}
+
+void svi_ls_destroy(svi_ls *h) {
+  if (!h) return;
+  DeviceGuard guard(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_all(h);
+  delete h;
+}
+
+int svi_ls_set_stream(svi_ls *h, void *cuda_stream) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  h->stream = (cudaStream_t)cuda_stream;
+  return SVI_OK;
+}
+
+int svi_ls_sync(svi_ls *h) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  return SVI_OK;
+}
+
+int svi_ls_set_state(svi_ls *h, const double *gamma, const double *lambda) {
+  if (!h || !gamma || !lambda) return fail(SVI_ERR_INVALID, "svi_ls_set_state: null argument");
+  DeviceGuard guard(h->device);
+  const Params &P = h->P;
+  const size_t nk = (size_t)P.n * P.k;
+  if (P.ld == P.k) {
+    CK(cudaMemcpyAsync(h->d_gamma, gamma, nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    int rc = ensure_stage(h, nk);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_stage, gamma, nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    svi::k_pad_rows<<<h->sms * 8, 256, 0, h->stream>>>(h->d_stage, h->d_gamma, P.n, P.k, P.ld);
+  }
+  CK(cudaMemcpyAsync(h->d_lambda, lambda, 2 * (size_t)P.k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  // expectations for ALL rows (a shard still needs its neighbours' factors before the first sweep)
+  Params all = P;
+  all.node_begin = 0;
+  all.node_end = P.n;
+  h->ops.refresh(all, h->stream, false);
+  h->ops.lambda(P, h->stream, 0, 0);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));   // host buffers may be pageable: do not return early
+  return SVI_OK;
+}
+
+int svi_ls_get_state(svi_ls *h, double *gamma, double *lambda) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  const Params &P = h->P;
+  const size_t nk = (size_t)P.n * P.k;
+  if (gamma) {
+    if (P.ld == P.k) {
+      CK(cudaMemcpyAsync(gamma, h->d_gamma, nk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    } else {
+      int rc = ensure_stage(h, nk);
+      if (rc) return rc;
+      svi::k_unpad_rows<<<h->sms * 8, 256, 0, h->stream>>>(h->d_gamma, h->d_stage, P.n, P.k, P.ld);
+      CK(cudaMemcpyAsync(gamma, h->d_stage, nk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
+  if (lambda)
+    CK(cudaMemcpyAsync(lambda, h->d_lambda, 2 * (size_t)P.k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SVI_OK;
+}
+
+int svi_ls_set_converged(svi_ls *h, const uint32_t *converged) {
+  if (!h || !converged) return fail(SVI_ERR_INVALID, "svi_ls_set_converged: null argument");
+  DeviceGuard guard(h->device);
+  CK(cudaMemcpyAsync(h->d_conv, converged, (size_t)h->P.n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SVI_OK;
+}
+
+int svi_ls_get_converged(svi_ls *h, uint32_t *converged, uint32_t *active_comms) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  if (converged)
+    CK(cudaMemcpyAsync(converged, h->d_conv, (size_t)h->P.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (active_comms)
+    CK(cudaMemcpyAsync(active_comms, h->d_active, (size_t)h->P.n * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                       h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SVI_OK;
+}
+
+int svi_ls_phase_phi(svi_ls *h, uint32_t iter, int write_comm) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  const Params &P = h->P;
+  if (write_comm)  // _communities.clear(); _fmap.zero()  (src/linksampling.cc:584-587)
+    CK(cudaMemsetAsync(h->d_mbits, 0, (size_t)P.n * P.words * sizeof(uint32_t), h->stream));
+  h->ops.phi(P, h->stream, iter > 1000 && P.k_div10 > 0, write_comm != 0);
+  CK(cudaGetLastError());
+  return SVI_OK;
+}
+
+int svi_ls_phase_node(svi_ls *h) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  const Params &P = h->P;
+  h->ops.node(P, h->stream, h->blocks_node);
+  svi::k_reduce_kpart<<<4, 256, 0, h->stream>>>(h->d_kpart, h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec,
+                                               h->d_kvec, P.ld);
+  CK(cudaGetLastError());
+  return SVI_OK;
+}
+
+int svi_ls_phase_s3(svi_ls *h) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  const Params &P = h->P;
+  h->ops.s3(P, h->stream, h->blocks_s3);
+  svi::k_reduce_kpart<<<2, 256, 0, h->stream>>>(h->d_kpart, h->blocks_s3, 1, 2 * h->ops.lanes * h->ops.vec,
+                                               h->d_kvec + 3 * (size_t)P.ld, P.ld);
+  CK(cudaGetLastError());
+  return SVI_OK;
+}
+
+int svi_ls_phase_finish(svi_ls *h, int annealing) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  h->ops.lambda(h->P, h->stream, annealing, 1);
+  h->ops.refresh(h->P, h->stream, true);
+  CK(cudaGetLastError());
+  return SVI_OK;
+}
+
+int svi_ls_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
+  int rc;
+  if ((rc = svi_ls_phase_phi(h, iter, write_comm))) return rc;
+  if ((rc = svi_ls_phase_node(h))) return rc;
+  if ((rc = svi_ls_phase_s3(h))) return rc;
+  return svi_ls_phase_finish(h, annealing);
+}
+
+int svi_ls_get_membership(svi_ls *h, uint32_t *bits) {
+  if (!h || !bits) return fail(SVI_ERR_INVALID, "svi_ls_get_membership: null argument");
+  DeviceGuard guard(h->device);
+  CK(cudaMemcpyAsync(bits, h->d_mbits, (size_t)h->P.n * h->P.words * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SVI_OK;
+}
+
+int svi_ls_heldout(svi_ls *h, uint64_t npairs, const uint32_t *p, const uint32_t *q, const uint8_t *y,
+                   double epsilon, double *loglik) {
+  if (!h || (npairs && (!p || !q || !y || !loglik))) return fail(SVI_ERR_INVALID, "svi_ls_heldout: null argument");
+  if (!npairs) return SVI_OK;
+  DeviceGuard guard(h->device);
+  for (uint64_t i = 0; i < npairs; ++i)
+    if (p[i] >= h->P.n || q[i] >= h->P.n) return fail(SVI_ERR_INVALID, "svi_ls_heldout: pair %llu out of range",
+                                                      (unsigned long long)i);
+  // staging: [p | q] as uint32, y as bytes, out as double -- carve from one scratch allocation
+  const size_t bytes = npairs * (2 * sizeof(uint32_t) + sizeof(double)) + ((npairs + 7) & ~(size_t)7);
+  int rc = ensure_stage(h, (bytes + sizeof(double) - 1) / sizeof(double));
+  if (rc) return rc;
+  double *d_out = h->d_stage;
+  uint32_t *d_p = reinterpret_cast<uint32_t *>(d_out + npairs);
+  uint32_t *d_q = d_p + npairs;
+  uint8_t *d_y = reinterpret_cast<uint8_t *>(d_q + npairs);
+  CK(cudaMemcpyAsync(d_p, p, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_q, q, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_y, y, npairs, cudaMemcpyHostToDevice, h->stream));
+  h->ops.heldout(h->P, h->stream, npairs, d_p, d_q, d_y, epsilon, d_out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(loglik, d_out, npairs * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SVI_OK;
+}
+
+int svi_ls_get_kvectors(svi_ls *h, double *sum, double *s1, double *s2, double *s3) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  double *dst[4] = {sum, s1, s2, s3};
+  for (int v = 0; v < 4; ++v)
+    if (dst[v])
+      CK(cudaMemcpyAsync(dst[v], h->d_kvec + (size_t)v * h->P.ld, h->P.k * sizeof(double), cudaMemcpyDeviceToHost,
+                         h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SVI_OK;
+}
+
+int svi_ls_device_buffer(svi_ls *h, svi_buffer which, void **dev_ptr, uint64_t *ld) {
+  if (!h || !dev_ptr) return fail(SVI_ERR_INVALID, "svi_ls_device_buffer: null argument");
+  uint64_t l = h->P.ld;
+  switch (which) {
+    case SVI_BUF_EXPPI: *dev_ptr = h->d_b; break;
+    case SVI_BUF_MPHI: *dev_ptr = h->d_mphi; break;
+    case SVI_BUF_GAMMA: *dev_ptr = h->d_gamma; break;
+    case SVI_BUF_KVEC: *dev_ptr = h->d_kvec; break;
+    case SVI_BUF_CONVERGED: *dev_ptr = h->d_conv; l = 1; break;
+    case SVI_BUF_LAMBDA: *dev_ptr = h->d_lambda; l = 2; break;
+    case SVI_BUF_ACTIVE: *dev_ptr = h->d_active; l = 1; break;
+    case SVI_BUF_ACTIVE_BITS: *dev_ptr = h->d_abits; l = h->P.words; break;
+    case SVI_BUF_MEMBER_BITS: *dev_ptr = h->d_mbits; l = h->P.words; break;
+    default: return fail(SVI_ERR_INVALID, "svi_ls_device_buffer: unknown buffer %d", (int)which);
+  }
+  if (ld) *ld = l;
+  return SVI_OK;
+}
+
+int svi_ls_get_info(svi_ls *h, svi_ls_info *info) {
+  if (!h || !info) return fail(SVI_ERR_INVALID, "svi_ls_get_info: null argument");
+  info->half_edges_phi = h->he_phi;
+  info->half_edges_s3 = h->he_s3;
+  info->segments_phi = h->P.nseg;
+  info->segments_s3 = h->P.nseg3;
+  info->ld = h->P.ld;
+  info->seg_len = h->seg_len;
+  info->lanes = (uint32_t)h->ops.lanes;
+  info->vec = (uint32_t)h->ops.vec;
+  info->device_bytes = h->device_bytes;
+  info->kernels_per_step = 7;  // phi, node, reduce, s3, reduce, lambda, refresh
+  return SVI_OK;
+}
+
+}  // extern "C"
