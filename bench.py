@@ -1,0 +1,427 @@
+#!/usr/bin/env python3
+"""bench.py -- link-sampling edge-updates/sec on synthetic MMSB graphs (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2s|tiny] [--impl ours|reference]
+
+One "step" = one full variational iteration (phi sweep + mean indicators + s3 sweep + lambda finish +
+expectation refresh + prune == the loop body src/linksampling.cc:584-761) over ALL training links of the
+workload.  `value` = links x steps / device time, state resident in HBM.  `e2e` = the same step driven
+through the C ABI with HOST buffers: every step uploads gamma/lambda from pinned memory
+(svi_ls_set_state), runs svi_ls_step, evaluates the held-out likelihood (svi_ls_heldout, the "loss" the
+reference computes every iteration, src/linksampling.cc:778-780) and downloads gamma/lambda
+(svi_ls_get_state).
+
+Under torchrun (N > 1) every rank owns an edge-balanced node block (svinet_b200/sharded.py); timing is
+CUDA events on the launching stream, max over ranks.
+
+`--impl reference` times the UNMODIFIED reference binary (oracle/_ref/svinet_ref, 1 thread -- the
+reference path is serial) on a bounded sample of the same workload; if the binary is absent it falls
+back to the oracle port.  That arm and the `cpu_baseline` leg are the only places this file touches
+oracle/.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (n, k, links)          BASELINE.json configs[3] is the one the metric is quoted on
+    "c4": (1_000_000, 200, 100_000_000),
+    "c3": (100_000, 100, 5_000_000),
+    "c2s": (17_903, 20, 196_972),          # AstroPh-shaped synthetic
+    "tiny": (2_000, 20, 20_000),
+}
+METRIC = "link_sampling_edge_updates_per_sec"
+UNIT = "edge-updates/s"
+
+
+def measured_peak_hbm():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background during the timed region)
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        if not shutil.which("nvidia-smi"):
+            return
+        fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+        os.close(fd)
+        self.f = open(self.path, "w")
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                     stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, reasons, smax, pw = [], set(), None, []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+                pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw) if pw else None)
+        return out
+
+
+# --------------------------------------------------------------------------------------------
+def fast_state(n, k, links, seed=5):
+    """Synthetic gamma shaped like init_gamma2's (every link adds a normalised uniform K-vector to both
+    endpoints, src/linksampling.cc:374-401): row p ~ deg(p)/K * (1 + noise).  lambda = eta = (1,1)."""
+    deg = np.bincount(links.ravel().astype(np.int64), minlength=n).astype(np.float64)
+    rng = np.random.default_rng(seed)
+    gamma = np.empty((n, k), dtype=np.float64)
+    step = max(1, (1 << 25) // k)
+    for s in range(0, n, step):
+        e = min(n, s + step)
+        gamma[s:e] = (deg[s:e, None] / k) * (1.0 + 0.2 * rng.random((e - s, k))) + 1.0 / k
+    return gamma, np.ones((k, 2), dtype=np.float64)
+
+
+def heldout_pairs(n, links, count, seed=11):
+    """`count` held-out pairs, half links half random non-link candidates (like the reference's 1% set)."""
+    rng = np.random.default_rng(seed)
+    half = max(1, count // 2)
+    li = links[rng.integers(0, links.shape[0], half)]
+    p = rng.integers(0, n, half).astype(np.uint32)
+    q = ((p.astype(np.int64) + 1 + rng.integers(0, n - 1, half)) % n).astype(np.uint32)
+    pp = np.concatenate([li[:, 0], np.minimum(p, q)]).astype(np.uint32)
+    qq = np.concatenate([li[:, 1], np.maximum(p, q)]).astype(np.uint32)
+    yy = np.concatenate([np.ones(half, np.uint8), np.zeros(half, np.uint8)])
+    return pp, qq, yy
+
+
+def phi_kernel_bytes(info, k):
+    """Algorithmic bytes of ONE phi-sweep launch of this implementation:
+    per half-edge one neighbour row (ld*8) + its column index (4) + its converged flag (4);
+    per segment one self row read (ld*8) + one partial row written (ld*8)."""
+    ld = info["ld"]
+    return info["half_edges_phi"] * (ld * 8 + 8) + info["segments_phi"] * (2 * ld * 8 + 12)
+
+
+def step_bytes_survey(nlinks, n, k, s=8):
+    """bytes_iter = nlinks*(6*K*s+16) + 7*N*K*s (push-form accounting)."""
+    return nlinks * (6 * k * s + 16) + 7 * n * k * s
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from svinet_b200 import synth
+    from svinet_b200.engine import LinkSamplingEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, k, target = WORKLOADS[args.workload]
+    t0 = time.time()
+    links = synth.mmsb_links(n, k, target, seed=1234, device=str(dev))      # identical on every rank
+    torch.cuda.empty_cache()
+    nlinks = links.shape[0]
+    gamma0, lam0 = fast_state(n, k, links)
+    t_gen = time.time() - t0
+
+    stream = torch.cuda.current_stream()
+    t0 = time.time()
+    if world == 1:
+        eng = LinkSamplingEngine(n, k, links, device=local_rank, stream=stream.cuda_stream)
+        runner = None
+        eng.set_state(gamma0, lam0)
+        step = lambda it: eng.step(it, True, it > 0)
+    else:
+        from svinet_b200.sharded import ShardedLinkSampling
+        runner = ShardedLinkSampling(n, k, links, rank=rank, world=world, device=local_rank,
+                                     stream=stream.cuda_stream)
+        eng = runner.eng
+        runner.set_state(gamma0, lam0)
+        step = lambda it: runner.step(it, True, it > 0)
+    info = eng.info()
+    t_create = time.time() - t0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    it = 0
+    for _ in range(args.warmup):
+        step(it); it += 1
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        if world == 1:
+            ev[s][0].record(stream)
+            eng.phase_phi(it, it > 0); ev[s][1].record(stream)
+            eng.phase_node(); ev[s][2].record(stream)
+            eng.phase_s3(); ev[s][3].record(stream)
+            eng.phase_finish(True); ev[s][4].record(stream)
+        else:
+            ev[s][0].record(stream)
+            runner.step(it, True, it > 0, events=ev[s])
+            ev[s][4].record(stream)
+        it += 1
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    total_ms = ev[0][0].elapsed_time(ev[-1][4])
+    if world == 1:
+        phase_ms = [float(np.mean([ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)])) for i in range(4)]
+    else:
+        phase_ms = runner.phase_ms(ev)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = nlinks * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the C ABI with host buffers (rank-local state up + down every step) ----
+    e2e = None
+    if world == 1:
+        pin_g = torch.empty((n, k), dtype=torch.float64).pin_memory()
+        pin_l = torch.empty((k, 2), dtype=torch.float64).pin_memory()
+        eng.get_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
+        hp, hq, hy = heldout_pairs(n, links, max(2, min(nlinks // 100, 2_000_000)))
+        e2e_steps = max(1, min(args.steps, 5))
+        for w in range(1):
+            eng.set_state_ptr(pin_g.data_ptr(), pin_l.data_ptr()); eng.step(it, True, True)
+            eng.heldout(hp, hq, hy); eng.get_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(e2e_steps):
+            eng.set_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
+            eng.step(it, True, True); it += 1
+            ll = eng.heldout(hp, hq, hy)
+            eng.get_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        state_bytes = (n * k + 2 * k) * 8
+        e2e = {"value": nlinks * e2e_steps / dt, "unit": UNIT, "steps": e2e_steps,
+               "h2d_bytes_per_step": state_bytes + hp.nbytes + hq.nbytes + hy.nbytes,
+               "d2h_bytes_per_step": state_bytes + ll.nbytes,
+               "what": "svi_ls_set_state(pinned host) + svi_ls_step + svi_ls_heldout + svi_ls_get_state(pinned host)",
+               "heldout_mean_loglik": float(ll.mean())}
+        del pin_g, pin_l
+    else:
+        e2e = runner.e2e(step_fn=step, it0=it, steps=max(1, min(args.steps, 5)), nlinks=nlinks, unit=UNIT)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak_hbm()
+    phi_bytes = phi_kernel_bytes(info, k)
+    phi_gbs = phi_bytes / (phase_ms[0] * 1e-3) / 1e9
+    survey_gbs = step_bytes_survey(nlinks, n, k) * args.steps / (total_ms * 1e-3) / 1e9 / max(world, 1)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: synthetic MMSB n=%d k=%d links=%d (BASELINE.json configs[3])" % (
+                       args.workload, n, k, nlinks) if args.workload == "c4" else
+                   "%s: synthetic MMSB n=%d k=%d links=%d" % (args.workload, n, k, nlinks),
+                   "n": n, "k": k, "links": int(nlinks), "annealing": True, "write_comm": True,
+                   "parallelism": "node-block shards x%d" % world if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (state %.2f GB per matrix), no flush" % (n * info["ld"] * 8 / 1e9)
+                   if n * info["ld"] * 8 > 200e6 else "state fits L2; not flushed between steps (iterative workload)",
+                   "seg_len": info["seg_len"], "tile": "G%d x V%d" % (info["lanes"], info["vec"])},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": info["kernels_per_step"] * args.steps,
+        "phase_ms": {"phi": phase_ms[0], "node": phase_ms[1], "s3": phase_ms[2], "finish": phase_ms[3]},
+        "roofline": {"bound": "hbm", "kernel": "k_phi", "achieved": phi_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": phi_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(phi_bytes),
+                     "note": "pull-form bytes of this kernel (DESIGN.md section 4)",
+                     "step_gbs_survey_8d_formula": survey_gbs,
+                     "step_frac_survey_8d_formula": survey_gbs / peak},
+        "setup_s": {"generate": t_gen, "create+upload": t_create},
+        "wall_s_timed_region": t_wall,
+    }
+    traffic_file = os.path.join(REPO, "profiles", "k_phi_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            tf = json.load(open(traffic_file))
+            if tf.get("workload") == args.workload:
+                out["roofline"]["traffic"] = tf.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_port(k, budget_s=args.cpu_budget)
+    print(json.dumps(out))
+    sys.stdout.flush()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+def sample_graph(k, nlinks_sample, avg_deg=200):
+    """A bounded sample of the workload for CPU timing: same generator, same K, same average degree."""
+    from svinet_b200 import synth
+    n_s = max(64, int(2 * nlinks_sample / avg_deg))
+    links = synth.mmsb_links(n_s, k, nlinks_sample, seed=4321, device="cpu")
+    return n_s, links
+
+
+def cpu_baseline_port(k, budget_s=20.0):
+    """Oracle (C restatement, 1 thread) on a bounded sample; `value` in the bench's unit."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import oracle_py as orc
+    per_edge_k = 6e-8                                   # ~54-60 ns per (edge,k) on the survey's Xeon
+    sweeps = 2
+    ns = int(max(2000, min(2_000_000, budget_s / (sweeps * per_edge_k * k))))
+    n_s, links = sample_graph(k, ns)
+    gamma, lam = fast_state(n_s, k, links)
+    st = orc.State.alloc(n_s, k, links.shape[0])
+    c = st.c
+    c.alpha, c.eta0, c.eta1, c.ones = 1.0 / k, 1.0, 1.0, links.shape[0]
+    st.arr("links")[:] = links
+    tl = np.zeros(n_s); np.add.at(tl, links.ravel().astype(np.int64), 2.0)
+    st.arr("tl")[:] = tl
+    st.arr("gamma")[:] = gamma; st.arr("gammanext")[:] = c.alpha
+    st.arr("lambda_")[:] = lam; st.arr("lambdanext")[:] = lam
+    st.refresh_expectations()
+    st.step(0, 1, 0)                                   # warm
+    t0 = time.perf_counter()
+    for i in range(sweeps):
+        st.step(1 + i, 1, 1)
+    dt = time.perf_counter() - t0
+    st.free()
+    return {"value": links.shape[0] * sweeps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle/oracle_ls.c, %d sweeps over a synthetic MMSB sample n=%d k=%d links=%d "
+                      "(same generator and average degree as the workload)" % (sweeps, n_s, k, links.shape[0]),
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation on this box's host cores, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, k, _ = WORKLOADS[args.workload]
+    ref_bin = os.path.join(REPO, "oracle", "_ref", "svinet_ref")
+    budget = args.ref_budget
+    sweeps_total = 2 * args.warmup + args.steps + 2      # two runs: M1 = warmup, M2 = warmup + steps (+1 each)
+    per_edge_k = 6e-8
+    ns = int(max(2000, min(1_000_000, budget / (sweeps_total * per_edge_k * k))))
+    n_s, links = sample_graph(k, ns)
+    if os.path.exists(ref_bin):
+        d = tempfile.mkdtemp(prefix="refarm_")
+        try:
+            # ids are written 1-based in link order so the reference sees exactly n_s distinct nodes
+            used = np.unique(links)
+            remap = np.zeros(n_s, dtype=np.int64); remap[used] = np.arange(used.size)
+            np.savetxt(os.path.join(d, "g.txt"), remap[links.astype(np.int64)], fmt="%d", delimiter="\t")
+            def run(m):
+                t0 = time.perf_counter()
+                subprocess.check_call([ref_bin, "-file", "g.txt", "-n", str(used.size), "-k", str(k), "-link-sampling",
+                                       "-rfreq", "100000", "-accuracy", "-max-iterations", str(m), "-no-stop"],
+                                      cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                return time.perf_counter() - t0
+            m1 = max(1, args.warmup)
+            m2 = m1 + args.steps
+            t1, t2 = run(m1), run(m2)
+            per_step = (t2 - t1) / args.steps
+            kind, cores = "reference", 1
+            sample = ("oracle/_ref/svinet_ref (unmodified reference, g++ -O2, 1 thread: the path is serial) "
+                      "-link-sampling -accuracy -rfreq 100000 on a synthetic MMSB sample n=%d k=%d links=%d; "
+                      "per-step = (wall(M=%d) - wall(M=%d)) / %d, cancelling the constructor"
+                      % (used.size, k, links.shape[0], m2, m1, args.steps))
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    else:
+        cb = cpu_baseline_port(k, budget_s=budget / 4)
+        per_step = links.shape[0] / cb["value"]
+        kind, cores, sample = "port", 1, cb["sample"] + " (oracle/_ref absent: oracle port)"
+        links = links[: int(cb["value"] * per_step)]
+    value = links.shape[0] / per_step
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "%s: synthetic MMSB n=%d k=%d (bounded sample of it: links=%d)" % (
+               args.workload, n, k, links.shape[0]), "k": k},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                            "host_cpus": os.cpu_count()},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the --impl reference arm")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,7 +42,10 @@ def compare_sweep(eng, st, tag, tol=TOL, check_member=False):
     conv, act = eng.get_converged()
     errs = {"gamma": rel_err(g, st.arr("gamma")), "lambda": rel_err(lam, st.arr("lambda_"))}
     for name in ("sum", "s1", "s2", "s3"):
-        errs[name] = rel_err(kv[name], st.arr(name), floor=1e-12)
+        # column sums feed lambda as eta + (...): what matters is the error relative to the vector's scale
+        # (a community holding ~1e-11 of the mass suffers (alpha + x) - alpha cancellation in BOTH codes)
+        want = st.arr(name)
+        errs[name] = rel_err(kv[name], want, floor=max(1e-12, 1e-6 * float(np.max(np.abs(want), initial=0.0))))
     for name, e in errs.items():
         assert e <= tol, "%s: %s rel err %.3e" % (tag, name, e)
     assert np.array_equal(conv, st.arr("converged")), "%s: converged differs" % tag
@@ -73,7 +76,9 @@ def run_model_lockstep(g, k, sweeps, tol=TOL, **opts):
         y = np.array([g.y(int(a), int(b)) for a, b in vp], dtype=np.uint8)
         got = eng.heldout(vp[:, 0], vp[:, 1], y)
         want = np.array([st.edge_likelihood(int(a), int(b), int(yy)) for (a, b), yy in zip(vp, y)])
-        assert rel_err(got, want) <= tol
+        # log-likelihoods are averaged by the caller: an absolute floor is the meaningful metric for the
+        # near-zero ones (log(1 - 1e-6) is ill-conditioned in relative terms)
+        assert rel_err(got, want, floor=1e-3) <= tol
     eng.close()
     m.close()
     return worst
@@ -292,7 +297,7 @@ def test_heldout_matches_literal_double_sum():
     y = rng.integers(0, 2, 500).astype(np.uint8)
     got = eng.heldout(p, q, y)
     want = np.array([st.edge_likelihood(int(a), int(b), int(c)) for a, b, c in zip(p, q, y)])
-    assert rel_err(got, want) <= TOL
+    assert rel_err(got, want, floor=1e-3) <= TOL
     eng.close(); st.free()
 
 
