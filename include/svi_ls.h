@@ -147,7 +147,9 @@ typedef struct svi_ls_info {
   uint64_t half_edges_phi, half_edges_s3, segments_phi, segments_s3;
   uint32_t ld;            /* padded row length (elements)                              */
   uint32_t seg_len;
-  uint32_t lanes, vec;    /* kernel tiling actually selected for this K                */
+  uint32_t lanes, vec;    /* sweep-kernel tiling selected for this K (lanes per segment,  */
+                          /* 16-byte vectors per lane)                                    */
+  uint32_t ring_depth;    /* rows in flight per group in the TMA ring sweeps (0 = unused) */
   uint64_t device_bytes;  /* HBM allocated by the handle                               */
   uint32_t kernels_per_step;
 } svi_ls_info;

@@ -5,6 +5,7 @@
 // needs the GPU fails with SVI_ERR_CUDA when there is none.
 #include "../../include/svi_ls.h"
 #include "svi_ls_kernels.cuh"
+#include "svi_ls_ring.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -47,6 +48,11 @@ struct Ops {
   int (*max_blocks_node)(int sms);
   int (*max_blocks_s3)(int sms);
   int lanes, vec, logdom;
+  // second-generation sweeps (svi_ls_ring.cuh), present for 32 < K <= 256
+  void (*phi_ring)(const Params &, cudaStream_t, bool sparse, bool comm) = nullptr;
+  void (*s3_ring)(const Params &, cudaStream_t, uint32_t blocks) = nullptr;
+  int (*max_blocks_s3_ring)(int sms, uint32_t ld) = nullptr;
+  int ring_lanes = 0, ring_vec = 0, ring_depth = 0, ring_threads = 256;
 };
 
 constexpr int kThreads = 256;
@@ -100,6 +106,91 @@ struct Tile {
   }
 };
 
+// ring sweeps: G lanes per segment, V double2 per lane, R rows in flight per group, T threads per block
+template <int G, int V, int R, int T>
+struct RingTile {
+  static constexpr int GPB = T / G;
+  static constexpr int CAP = 2 * G * V;
+  static constexpr size_t kSmem = (size_t)GPB * R * (CAP * 8 + 8);
+  template <class K>
+  static void prep(K kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+  }
+  static void phi(const Params &P, cudaStream_t st, bool sparse, bool comm) {
+    if (!P.nseg) return;
+    const uint32_t blocks = (uint32_t)(((uint64_t)P.nseg * G + T - 1) / T);
+    using svi::Sweep;
+#define SVI_RING_PHI(S, C)                                                         \
+  do {                                                                             \
+    auto kern = svi::k_sweep_ring<G, V, R, T, Sweep::Phi, S, C>;                   \
+    prep(kern);                                                                    \
+    kern<<<blocks, T, kSmem, st>>>(P);                                             \
+  } while (0)
+    if (sparse && comm) SVI_RING_PHI(true, true);
+    else if (sparse) SVI_RING_PHI(true, false);
+    else if (comm) SVI_RING_PHI(false, true);
+    else SVI_RING_PHI(false, false);
+#undef SVI_RING_PHI
+  }
+  static void s3(const Params &P, cudaStream_t st, uint32_t blocks) {
+    auto kern = svi::k_sweep_ring<G, V, R, T, svi::Sweep::S3, false, false>;
+    prep(kern);
+    kern<<<blocks, T, kSmem, st>>>(P);
+  }
+  static int max_blocks_s3(int sms, uint32_t) {
+    auto kern = svi::k_sweep_ring<G, V, R, T, svi::Sweep::S3, false, false>;
+    prep(kern);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, kSmem) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    return per_sm * sms;
+  }
+  static void attach(Ops *o) {
+    o->phi_ring = phi;
+    o->s3_ring = s3;
+    o->max_blocks_s3_ring = max_blocks_s3;
+    o->ring_lanes = G;
+    o->ring_vec = V;
+    o->ring_depth = R;
+    o->ring_threads = T;
+  }
+};
+
+void pick_ring(uint32_t k, Ops *o) {
+  const char *off = getenv("SVI_LS_DISABLE_RING");
+  if (off && off[0] == '1') return;
+  const char *gsel = getenv("SVI_LS_RING_G");   // development A/B switch: 8 or 16
+  const int want_g = gsel ? atoi(gsel) : 0;
+  const uint32_t ld = (k + 3u) & ~3u;
+  if (k <= 32 || k > 256) return;
+  if (ld <= 112) {   // G = 8, V = ceil(ld/16)
+    switch ((ld + 15) / 16) {
+      case 3: RingTile<8, 3, 2, 256>::attach(o); break;
+      case 4: RingTile<8, 4, 2, 256>::attach(o); break;
+      case 5: RingTile<8, 5, 2, 256>::attach(o); break;
+      case 6: RingTile<8, 6, 2, 256>::attach(o); break;
+      default: RingTile<8, 7, 2, 256>::attach(o); break;
+    }
+  } else if (ld <= 208 && want_g != 16) {   // G = 8, V = ceil(ld/16) in 8..13
+    switch ((ld + 15) / 16) {
+      case 8: RingTile<8, 8, 2, 128>::attach(o); break;
+      case 9: RingTile<8, 9, 2, 128>::attach(o); break;
+      case 10: RingTile<8, 10, 2, 128>::attach(o); break;
+      case 11: RingTile<8, 11, 2, 128>::attach(o); break;
+      case 12: RingTile<8, 12, 2, 128>::attach(o); break;
+      default: RingTile<8, 13, 2, 128>::attach(o); break;
+    }
+  } else {   // G = 16, V = ceil(ld/32) in 4..8
+    switch ((ld + 31) / 32) {
+      case 4: RingTile<16, 4, 4, 256>::attach(o); break;
+      case 5: RingTile<16, 5, 4, 256>::attach(o); break;
+      case 6: RingTile<16, 6, 4, 256>::attach(o); break;
+      case 7: RingTile<16, 7, 4, 256>::attach(o); break;
+      default: RingTile<16, 8, 4, 256>::attach(o); break;
+    }
+  }
+}
+
 // K -> tiling.  Factorised (exp-domain) rows up to K = 256; log-domain above (underflow, see .cuh)
 bool pick_ops(uint32_t k, Ops *o) {
   if (k == 0) return false;
@@ -116,6 +207,7 @@ bool pick_ops(uint32_t k, Ops *o) {
   else if (k <= 768) *o = Tile<32, 12, true>::ops();
   else if (k <= 1024) *o = Tile<32, 16, true>::ops();
   else return false;
+  pick_ring(k, o);
   return true;
 }
 
@@ -310,10 +402,15 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   const size_t nld = (size_t)n * ld;
   h->blocks_node = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ops.max_blocks_node(h->sms),
                                                                    ((int64_t)nlocal * ops.lanes + kThreads - 1) / kThreads));
-  h->blocks_s3 = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ops.max_blocks_s3(h->sms),
-                                                                 ((int64_t)nseg3 * ops.lanes + kThreads - 1) / kThreads));
+  if (ops.s3_ring)
+    h->blocks_s3 = (uint32_t)std::max<int64_t>(
+        1, std::min<int64_t>(ops.max_blocks_s3_ring(h->sms, ld),
+                             ((int64_t)nseg3 * ops.ring_lanes + ops.ring_threads - 1) / ops.ring_threads));
+  else
+    h->blocks_s3 = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ops.max_blocks_s3(h->sms),
+                                                                   ((int64_t)nseg3 * ops.lanes + kThreads - 1) / kThreads));
   h->kpart_blocks = std::max(h->blocks_node, h->blocks_s3);
-  const size_t cap = 2 * (size_t)ops.lanes * ops.vec;
+  const size_t cap = std::max(2 * (size_t)ops.lanes * ops.vec, 2 * (size_t)ops.ring_lanes * ops.ring_vec);
   cudaError_t e = cudaSuccess;
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   A(dalloc(&h->d_col, col.size(), &tot));
@@ -471,7 +568,8 @@ int svi_ls_phase_phi(svi_ls *h, uint32_t iter, int write_comm) {
   const Params &P = h->P;
   if (write_comm)  // _communities.clear(); _fmap.zero()  (src/linksampling.cc:584-587)
     CK(cudaMemsetAsync(h->d_mbits, 0, (size_t)P.n * P.words * sizeof(uint32_t), h->stream));
-  h->ops.phi(P, h->stream, iter > 1000 && P.k_div10 > 0, write_comm != 0);
+  if (h->ops.phi_ring) h->ops.phi_ring(P, h->stream, iter > 1000 && P.k_div10 > 0, write_comm != 0);
+  else h->ops.phi(P, h->stream, iter > 1000 && P.k_div10 > 0, write_comm != 0);
   CK(cudaGetLastError());
   return SVI_OK;
 }
@@ -491,9 +589,14 @@ int svi_ls_phase_s3(svi_ls *h) {
   if (!h) return fail(SVI_ERR_INVALID, "null handle");
   DeviceGuard guard(h->device);
   const Params &P = h->P;
-  h->ops.s3(P, h->stream, h->blocks_s3);
-  svi::k_reduce_kpart<<<2, 256, 0, h->stream>>>(h->d_kpart, h->blocks_s3, 1, 2 * h->ops.lanes * h->ops.vec,
-                                               h->d_kvec + 3 * (size_t)P.ld, P.ld);
+  uint32_t cap3 = 2 * h->ops.lanes * h->ops.vec;
+  if (h->ops.s3_ring) {
+    h->ops.s3_ring(P, h->stream, h->blocks_s3);
+    cap3 = 2 * h->ops.ring_lanes * h->ops.ring_vec;
+  } else {
+    h->ops.s3(P, h->stream, h->blocks_s3);
+  }
+  svi::k_reduce_kpart<<<2, 256, 0, h->stream>>>(h->d_kpart, h->blocks_s3, 1, cap3, h->d_kvec + 3 * (size_t)P.ld, P.ld);
   CK(cudaGetLastError());
   return SVI_OK;
 }
@@ -589,8 +692,9 @@ int svi_ls_get_info(svi_ls *h, svi_ls_info *info) {
   info->segments_s3 = h->P.nseg3;
   info->ld = h->P.ld;
   info->seg_len = h->seg_len;
-  info->lanes = (uint32_t)h->ops.lanes;
-  info->vec = (uint32_t)h->ops.vec;
+  info->lanes = (uint32_t)(h->ops.phi_ring ? h->ops.ring_lanes : h->ops.lanes);
+  info->vec = (uint32_t)(h->ops.phi_ring ? h->ops.ring_vec : h->ops.vec);
+  info->ring_depth = (uint32_t)h->ops.ring_depth;
   info->device_bytes = h->device_bytes;
   info->kernels_per_step = 7;  // phi, node, reduce, s3, reduce, lambda, refresh
   return SVI_OK;

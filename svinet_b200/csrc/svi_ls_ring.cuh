@@ -1,0 +1,313 @@
+// svi_ls_ring.cuh -- the two edge sweeps (phi, s3) for 32 < K <= 256, second generation.
+//
+// What the first-generation kernels (svi_ls_kernels.cuh: k_phi, k_s3) left on the table
+// (profiles/r01_v1_k_phi_c4_ncu_full.txt: 246 warp-instructions per neighbour, 12 resident warps/SM,
+// long_scoreboard on a serialised col -> converged -> row load chain, 2.78 TB/s):
+//   * rows now travel global -> shared through the TMA bulk-copy engine (cp.async.bulk, SASS UBLKCP)
+//     into a per-group ring of R slots, each completed on its own mbarrier; the ring keeps R rows in
+//     flight per group without spending registers on them
+//   * neighbour ids and their converged flags are fetched one CHUNK (G neighbours, coalesced) ahead,
+//     so the dependent-load chain is paid once per G neighbours instead of once per neighbour
+//   * a group is G = 8 or 16 lanes (not a full warp): the per-neighbour reductions, reciprocal and
+//     arg-max butterflies are issued once per WARP instruction and serve 32/G neighbours; the groups
+//     of a warp run in lockstep over a common trip count, and when every group of the warp is on the
+//     full-phi branch (the common case) the body runs warp-converged with full-mask shuffles
+//   * w[k] = (b[p][k]*eb[k]) * b[q][k]: the self factor is folded once per segment, the accumulate is
+//     one DFMA; ring slots are padded to the tile width and the pad is zeroed once, so row reads from
+//     shared memory are unpredicated LDS.128
+#pragma once
+#include "svi_ls_kernels.cuh"
+
+namespace svi {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (complete_tx)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ double2 lds2(uint32_t addr) {
+  double2 r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+  return r;
+}
+
+template <int G>
+__device__ __forceinline__ uint32_t warp_max_over_groups(uint32_t v) {
+#pragma unroll
+  for (int o = G; o < 32; o <<= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Per-group view of the ring.  Slot s of this group: rows + s*slot_bytes, barrier bars + 8*s.
+template <int R>
+struct Ring {
+  uint32_t rows, bars, row_bytes, slot_bytes;
+  uint32_t phase;  // bit s = parity the next wait on slot s must see
+  __device__ __forceinline__ void issue(uint32_t slot, const double *src) const {
+    mbar_expect_tx(bars + 8u * slot, row_bytes);
+    bulk_g2s(rows + slot * slot_bytes, src, row_bytes, bars + 8u * slot);
+  }
+  __device__ __forceinline__ void wait(uint32_t slot) {
+    const uint32_t par = (phase >> slot) & 1u;
+    while (!mbar_try_wait(bars + 8u * slot, par)) {
+    }
+    phase ^= 1u << slot;
+  }
+};
+
+enum class Sweep { Phi, S3 };
+
+// phi of one neighbour row sitting in shared memory at `rbase`, accumulated into acc (and the arg-max
+// community into mb).  `mask` is the shuffle mask: the full warp when every group of the warp is here,
+// the group's own lanes otherwise.
+template <int G, int V, bool SPARSE, bool COMM>
+__device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_t lane, unsigned mask,
+                                        const double2 (&be)[V], double2 (&acc)[V], uint32_t &mb, bool sparse,
+                                        uint32_t p, uint32_t q) {
+  double2 w[V];
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const double2 r = lds2(rbase + 16u * (lane + G * j));
+    w[j].x = be[j].x * r.x;
+    w[j].y = be[j].y * r.y;
+  }
+  if (SPARSE && sparse) {   // restrict to the union of the endpoints' active communities (:634-664)
+    const uint32_t *ap = P.abits + (size_t)p * P.words, *aq = P.abits + (size_t)q * P.words;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const uint32_t c = 2u * (lane + G * j);
+      uint32_t bits = 0;
+      if (c < P.k) bits = (ap[c >> 5] | aq[c >> 5]) >> (c & 31u);
+      if (!(bits & 1u)) w[j].x = 0.0;
+      if (!(bits & 2u)) w[j].y = 0.0;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) s += w[j].x + w[j].y;
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(mask, s, o);
+  // s == 0 only for an empty active union: phi stays all-zero (:634-664 with an empty list).  No early
+  // return: other groups of the warp may share the shuffles below.
+  const double inv = s > 0.0 ? 1.0 / s : 0.0;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    acc[j].x = fma(w[j].x, inv, acc[j].x);
+    acc[j].y = fma(w[j].y, inv, acc[j].y);
+  }
+  if (COMM) {
+    // arg-max of the unnormalised weights (same arg-max as phi = w/s); first maximum wins
+    // (D1Array::max, src/matrix.hh:521-532)
+    double best = 0.0;
+    uint32_t bestk = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const uint32_t c = 2u * (lane + G * j);
+      if (w[j].x > best) { best = w[j].x; bestk = c; }
+      if (w[j].y > best) { best = w[j].y; bestk = c + 1u; }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(mask, best, o);
+      const uint32_t ok = __shfl_xor_sync(mask, bestk, o);
+      if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+    }
+    if (best > 0.0 && lane == (bestk >> 5)) mb |= 1u << (bestk & 31u);
+  }
+}
+
+// One group per segment, 32/G segments per warp in lockstep.
+//   MODE == Phi : part[seg] = sum over the segment's neighbours of phi        (K1, src/linksampling.cc:605-725)
+//   MODE == S3  : block partials of s3[k] = sum mphi[p][k]*mphi[q][k]          (K3, :731-746)
+template <int G, int V, int R, int T, Sweep MODE, bool SPARSE, bool COMM>
+__global__ void __launch_bounds__(T) k_sweep_ring(const Params P) {
+  static_assert(R <= G && (R & (R - 1)) == 0, "ring depth: power of two, at most one chunk");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int GPB = T / G;        // groups per block
+  constexpr int CAP = 2 * G * V;    // columns covered by the tile (>= ld)
+  const unsigned gmask = group_mask<G>();
+  const uint32_t lane = threadIdx.x & (G - 1);
+  const uint32_t grp = threadIdx.x / G;
+  // smem: [GPB][R] slots of CAP doubles (the tail beyond ld stays zero), then [GPB][R] mbarriers
+  const uint32_t rows0 = smem_u32(smem_raw);
+  const uint32_t bars0 = rows0 + GPB * R * CAP * 8u;
+  Ring<R> ring;
+  ring.row_bytes = P.ld * 8u;
+  ring.slot_bytes = CAP * 8u;
+  ring.rows = rows0 + grp * R * CAP * 8u;
+  ring.bars = bars0 + grp * R * 8u;
+  ring.phase = 0;
+  // zero the pad columns [ld, CAP) of every slot once; the bulk copies only ever write [0, ld)
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(GPB * R * CAP); i += T)
+    if (i % CAP >= P.ld) reinterpret_cast<double *>(smem_raw)[i] = 0.0;
+  if (lane < R) mbar_init(ring.bars + 8u * lane, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const double *src_rows = MODE == Sweep::Phi ? P.b : P.mphi;
+  const uint32_t nseg = MODE == Sweep::Phi ? P.nseg : P.nseg3;
+  const uint32_t *seg_node = MODE == Sweep::Phi ? P.seg_node : P.seg3_node;
+  const uint32_t *seg_beg = MODE == Sweep::Phi ? P.seg_beg : P.seg3_beg;
+  const uint32_t *seg_cnt = MODE == Sweep::Phi ? P.seg_cnt : P.seg3_cnt;
+
+  double2 s3acc[V];  // S3 only: per-lane column sums across this group's segments
+#pragma unroll
+  for (int j = 0; j < V; ++j) s3acc[j] = make_double2(0.0, 0.0);
+
+  const uint32_t ggid = (blockIdx.x * T + threadIdx.x) / G;
+  const uint32_t ngroups = gridDim.x * T / G;
+  // Phi: one segment per group (grid covers nseg).  S3: persistent, grid-stride over segments.
+  const uint32_t warp_first = ggid - grp % (32 / G);   // first group id of this warp
+  for (uint32_t base = warp_first; base < nseg; base += ngroups) {
+    const uint32_t seg = base + grp % (32 / G);
+    const bool have = seg < nseg;
+    const uint32_t p = have ? seg_node[seg] : 0u;
+    const uint32_t beg = have ? seg_beg[seg] : 0u;
+    const uint32_t cnt = have ? seg_cnt[seg] : 0u;
+    const uint32_t cntmax = warp_max_over_groups<G>(cnt);
+    const uint32_t pc = have ? P.conv[p] : 0u;
+    uint32_t pa = 0;
+    if (SPARSE) pa = have ? P.active[p] : 0u;
+    const double *self_row = src_rows + (size_t)p * P.ld;
+
+    double2 be[V], acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const uint32_t c = 2u * (lane + G * j);
+      acc[j] = make_double2(0.0, 0.0);
+      if (MODE == Sweep::Phi) {
+        const double2 bs = have ? ld_row2(self_row, c, P.ld) : make_double2(0.0, 0.0);
+        const double2 eb = ld_row2(P.eb, c, P.ld);
+        be[j] = make_double2(bs.x * eb.x, bs.y * eb.y);
+      }
+    }
+    uint32_t mb = 0;        // Phi+COMM: membership word `lane`
+    double one_hot = 0.0;   // S3: shortcut mass for column pc-1
+
+    // chunk 0 ids, then the ring prologue
+    uint32_t q_cur = p, qc_cur = 0, q_nxt = p, qc_nxt = 0;
+    if (lane < cnt) {
+      q_cur = __ldg(P.col + beg + lane);
+      qc_cur = P.conv[q_cur];
+    }
+    if (lane < R && lane < cnt && !((pc != 0u) != (qc_cur != 0u)))
+      ring.issue(lane, src_rows + (size_t)q_cur * P.ld);
+
+    for (uint32_t c0 = 0; c0 < cntmax; c0 += G) {
+      if (c0 > 0) {
+        q_cur = q_nxt;
+        qc_cur = qc_nxt;
+      }
+      const bool nxt_live = c0 + G + lane < cnt;
+      q_nxt = nxt_live ? __ldg(P.col + beg + c0 + G + lane) : p;
+      qc_nxt = 0;
+      const uint32_t ulim = min((uint32_t)G, cntmax - c0);
+      for (uint32_t u = 0; u < ulim; ++u) {
+        const uint32_t i = c0 + u;
+        if (u == 1 || ulim == 1) qc_nxt = nxt_live ? P.conv[q_nxt] : 0u;   // chunk c+1 flags, one row late
+        // control flow is warp-uniform here: full-mask shuffles, each confined to its G-lane segment
+        const uint32_t q = __shfl_sync(0xffffffffu, q_cur, u, G);
+        const uint32_t qc = __shfl_sync(0xffffffffu, qc_cur, u, G);
+        const bool live = i < cnt;
+        const bool full = live && !((pc != 0u) != (qc != 0u));
+        const uint32_t slot = i & (R - 1);
+        const bool allfull = __all_sync(0xffffffffu, full);
+        const uint32_t rbase = ring.rows + slot * ring.slot_bytes;
+        if (full) ring.wait(slot);
+        if (MODE == Sweep::S3) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const double2 r = lds2(rbase + 16u * (lane + G * j));
+              acc[j].x += r.x;
+              acc[j].y += r.y;
+            }
+          } else if (live) {
+            if (pc) {          // s3[pc-1] += mphi[q][pc]  (sic, :739-740; column K reads as 0)
+              one_hot += pc < P.k ? P.mphi[(size_t)q * P.ld + pc] : 0.0;
+            } else {           // s3[qc-1] += mphi[p][qc]  (:741-742)
+              const double v = qc < P.k ? self_row[qc] : 0.0;
+              const uint32_t c = qc - 1u;
+#pragma unroll
+              for (int j = 0; j < V; ++j) {
+                const uint32_t c2 = 2u * (lane + G * j);
+                if (c == c2) s3acc[j].x += v;
+                if (c == c2 + 1u) s3acc[j].y += v;
+              }
+            }
+          }
+        } else {
+          bool sparse = false;
+          if (SPARSE) sparse = full && pa < P.k_div10 && P.active[q] < P.k_div10;
+          if (allfull) {
+            phi_row<G, V, SPARSE, COMM>(P, rbase, lane, 0xffffffffu, be, acc, mb, sparse, p, q);
+          } else if (full) {
+            phi_row<G, V, SPARSE, COMM>(P, rbase, lane, gmask, be, acc, mb, sparse, p, q);
+          } else if (live) {
+            const uint32_t c = (pc ? pc : qc) - 1u;   // one-hot phi, :622-631
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const uint32_t c2 = 2u * (lane + G * j);
+              if (c == c2) acc[j].x += 1.0;
+              if (c == c2 + 1u) acc[j].y += 1.0;
+            }
+          }
+        }
+        // refill this slot with neighbour i+R (its id sits in the current or the next chunk)
+        __syncwarp();
+        const uint32_t ua = u + R;
+        const uint32_t qa = __shfl_sync(0xffffffffu, ua < (uint32_t)G ? q_cur : q_nxt, ua & (G - 1), G);
+        const uint32_t qca = __shfl_sync(0xffffffffu, ua < (uint32_t)G ? qc_cur : qc_nxt, ua & (G - 1), G);
+        if (lane == 0 && i + R < cnt && !((pc != 0u) != (qca != 0u)))
+          ring.issue(slot, src_rows + (size_t)qa * P.ld);
+      }
+    }
+
+    if (MODE == Sweep::Phi) {
+      if (have) {
+        double *out = P.part + (size_t)seg * P.ld;
+#pragma unroll
+        for (int j = 0; j < V; ++j) st_row2(out, 2u * (lane + G * j), P.ld, acc[j]);
+        if (COMM && mb) atomicOr(P.mbits + (size_t)p * P.words + lane, mb);
+      }
+    } else if (have) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const uint32_t c = 2u * (lane + G * j);
+        const double2 mp = ld_row2(self_row, c, P.ld);
+        s3acc[j].x = fma(mp.x, acc[j].x, s3acc[j].x);
+        s3acc[j].y = fma(mp.y, acc[j].y, s3acc[j].y);
+        if (pc && pc - 1u == c) s3acc[j].x += one_hot;
+        if (pc && pc - 1u == c + 1u) s3acc[j].y += one_hot;
+      }
+    }
+  }
+  if (MODE == Sweep::S3) {
+    // all rings are drained here (every issued copy was waited on), so the rows area can be reused
+    block_reduce_columns<G, V>(s3acc, reinterpret_cast<double *>(smem_raw),
+                               P.kpart + (size_t)blockIdx.x * CAP);
+  }
+}
+
+}  // namespace svi

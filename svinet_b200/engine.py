@@ -26,7 +26,7 @@ class SviInfo(C.Structure):
     _fields_ = [("half_edges_phi", C.c_uint64), ("half_edges_s3", C.c_uint64),
                 ("segments_phi", C.c_uint64), ("segments_s3", C.c_uint64),
                 ("ld", C.c_uint32), ("seg_len", C.c_uint32), ("lanes", C.c_uint32), ("vec", C.c_uint32),
-                ("device_bytes", C.c_uint64), ("kernels_per_step", C.c_uint32)]
+                ("ring_depth", C.c_uint32), ("device_bytes", C.c_uint64), ("kernels_per_step", C.c_uint32)]
 
 
 class SviError(RuntimeError):
