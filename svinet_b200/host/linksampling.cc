@@ -1,0 +1,483 @@
+// linksampling.cc -- see linksampling.hh.  All file:line citations refer to the reference's
+// src/linksampling.cc unless another file is named.
+#include "linksampling.hh"
+
+#include <algorithm>
+#include <cassert>
+#include <cerrno>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <thread>
+
+namespace {
+
+[[noreturn]] void die_dev(const char *what) {
+  fprintf(stderr, "svinet: %s failed: %s\n", what, svi_ls_last_error());
+  exit(-1);
+}
+#define DEV(call) do { if ((call) != SVI_OK) die_dev(#call); } while (0)
+
+FILE *open_or_die(const std::string &path, const char *mode, const char *what) {
+  FILE *f = fopen(path.c_str(), mode);
+  if (!f) {
+    printf("cannot open %s file:%s\n", what, strerror(errno));
+    exit(-1);
+  }
+  return f;
+}
+
+// Format `rows` lines in parallel (each line built by `line(i, buf)`), write them in order.
+template <class F>
+void write_rows(FILE *f, uint32_t rows, F line) {
+  const uint32_t block = 1u << 15;
+  const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  for (uint32_t r0 = 0; r0 < rows; r0 += block) {
+    const uint32_t r1 = std::min(rows, r0 + block);
+    std::vector<std::string> out(nt);
+    std::vector<std::thread> th;
+    const uint32_t per = (r1 - r0 + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t] {
+        const uint32_t a = std::min(r1, r0 + t * per), b = std::min(r1, a + per);
+        for (uint32_t i = a; i < b; ++i) line(i, out[t]);
+      });
+    for (auto &x : th) x.join();
+    for (auto &s : out) fwrite(s.data(), 1, s.size(), f);
+  }
+}
+
+inline void append_fmt(std::string &s, const char *fmt, double v) {
+  char b[64];
+  const int len = snprintf(b, sizeof b, fmt, v);
+  s.append(b, (size_t)len);
+}
+
+}  // namespace
+
+LinkSampling::LinkSampling(Env &env, Network &network)
+    : env_(env), net_(network), n_(env.n), k_(env.k), rng_(0), start_time_(time(0)) {
+  total_pairs_ = (double)(uint32_t)(n_ * (n_ - 1) / 2);          // 32-bit product, :37
+  env_.plog("inference n", n_);
+  env_.plog("total pairs", total_pairs_);
+  ones_prob_ = double(net_.ones()) / total_pairs_;               // :49-50
+  zeros_prob_ = 1 - ones_prob_;
+  env_.plog("ones_prob", ones_prob_);
+  env_.plog("zeros_prob", zeros_prob_);
+  uint32_t maxdeg;
+  double avgdeg;
+  net_.deg_stats(maxdeg, avgdeg);
+  env_.plog("avg degree", avgdeg);
+  env_.plog("max degree", maxdeg);
+  {
+    // the K x 2 prior printed the way the reference's Matrix::s() prints it (src/matrix.hh:898-924)
+    std::ostringstream sa;
+    sa << "\n[ ";
+    for (uint32_t i = 0; i < std::min<uint32_t>(k_, 512); ++i) {
+      const double row[2] = {env_.eta0, env_.eta1};
+      for (int j = 0; j < 2; ++j) {
+        double u = row[j];
+        if (u < 1e-05 && u > .0) u = .0;
+        if (i > 0 && j == 0) sa << "  " << u << " ";
+        else sa << u << " ";
+      }
+      sa << "\n";
+    }
+    sa << "]";
+    env_.plog("eta", sa.str());
+  }
+  if (env_.seed) rng_.set((unsigned long)env_.seed);             // :74-75
+
+  FILE *vef = open_or_die(env_.file("/validation-edges.txt"), "w", "validation edges");
+  FILE *tef = open_or_die(env_.file("/test-edges.txt"), "w", "test edges");
+  fclose(tef);
+  if (!env_.load_heldout) {
+    env_.plog("load validation from file:", false);
+    init_validation();
+  } else {
+    env_.plog("load validation from file:", true);
+    load_validation();
+  }
+  for (const Edge &e : validation_pairs_)                        // edgelist_s, :190-206
+    fprintf(vef, "%d\t%d\t%d\n", net_.seq2id(e.first), net_.seq2id(e.second), (int)net_.y(e.first, e.second));
+  fprintf(vef, "\n");
+  fclose(vef);
+  if (env_.load_test) fprintf(stderr, "svinet: -load-test is accepted but the test set is not used in this build\n");
+
+  gamma_.assign((size_t)n_ * k_, 0.0);
+  lambda_.assign((size_t)k_ * 2, 0.0);
+  if (env_.model_load) {
+    if (load_model() < 0) exit(-1);
+  } else if (env_.use_init_communities) {
+    fprintf(stderr, "svinet: -init-communities is not part of this build\n");
+    exit(-1);
+  } else {
+    init_gamma2();
+    for (uint32_t c = 0; c < k_; ++c) {                          // init_lambda, :364-372
+      lambda_[2 * c] = env_.eta0;
+      lambda_[2 * c + 1] = env_.eta1;
+    }
+  }
+
+  tf_ = open_or_die(env_.file("/test.txt"), "w", "test");
+  vf_ = open_or_die(env_.file("/validation.txt"), "w", "validation");
+  env_.plog("network ones", net_.ones());
+  env_.plog("network singles", net_.singles());
+  lf_ = open_or_die(env_.file("/logl.txt"), "w", "logl");
+
+  assign_training_links();                                       // :566 (no RNG use, so it can run here)
+  if (env_.dump_only) return;
+
+  svi_ls_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.n = n_; cfg.k = k_; cfg.nlinks = links_.size() / 2;
+  cfg.alpha = env_.alpha; cfg.eta0 = env_.eta0; cfg.eta1 = env_.eta1;
+  cfg.ones = net_.ones(); cfg.device = -1; cfg.seg_len = 0;
+  cfg.node_begin = 0; cfg.node_end = n_;
+  DEV(svi_ls_create(&cfg, links_.data(), training_links_.data(), &dev_));
+  DEV(svi_ls_set_state(dev_, gamma_.data(), lambda_.data()));
+
+  // held-out pairs in std::map<Edge,bool> order (lexicographic), the order validation_likelihood sums in
+  validation_sorted_ = validation_pairs_;
+  std::sort(validation_sorted_.begin(), validation_sorted_.end());
+  for (const Edge &e : validation_sorted_) {
+    hp_.push_back(e.first);
+    hq_.push_back(e.second);
+    hy_.push_back(net_.y(e.first, e.second) ? 1 : 0);
+  }
+  hll_.resize(hp_.size());
+  validation_likelihood();                                       // :150
+  start_time_ = time(0);
+}
+
+LinkSampling::~LinkSampling() {
+  if (vf_) fclose(vf_);
+  if (tf_) fclose(tf_);
+  if (lf_) fclose(lf_);
+  if (dev_) svi_ls_destroy(dev_);
+}
+
+bool LinkSampling::edge_ok(const Edge &e) const {
+  if (e.first == e.second) return false;
+  return !std::binary_search(validation_sorted_.begin(), validation_sorted_.end(), e);
+}
+
+void LinkSampling::get_random_edge(bool link, Edge &e) {
+  if (!link) {
+    do {
+      e.first = (uint32_t)rng_.uniform_int(n_);
+      e.second = (uint32_t)rng_.uniform_int(n_);
+      Network::order_edge(e);
+    } while (!edge_ok(e));
+  } else {
+    do {
+      e = net_.edges()[rng_.uniform_int(net_.ones())];
+    } while (!edge_ok(e));
+  }
+}
+
+void LinkSampling::set_validation_sample(int s) {
+  int c0 = 0, c1 = 0;
+  const int p = s / 2;
+  while (c0 < p || c1 < p) {
+    Edge e;
+    get_random_edge(c0 == p, e);   // non-link candidates first, then links
+    const bool y = net_.y(e.first, e.second);
+    bool keep = false;
+    if (!y && c0 < p) { c0++; keep = true; }
+    if (y && c1 < p) { c1++; keep = true; }
+    if (keep) {
+      validation_pairs_.push_back(e);
+      validation_sorted_.insert(std::upper_bound(validation_sorted_.begin(), validation_sorted_.end(), e), e);
+    }
+  }
+}
+
+void LinkSampling::init_validation() {
+  const int s1 = (int)(env_.heldout_ratio * net_.ones());        // :167
+  set_validation_sample(s1);
+  env_.plog("heldout ratio", env_.heldout_ratio);
+  env_.plog("validation pairs (1s and 0s)", (uint64_t)validation_pairs_.size());
+}
+
+void LinkSampling::load_validation() {
+  FILE *f = fopen(env_.load_heldout_fname.c_str(), "r");
+  if (!f) {
+    fprintf(stderr, "error: cannot read test validation file %s\n", env_.load_heldout_fname.c_str());
+    exit(-1);
+  }
+  uint32_t a, b, cnt = 0;
+  while (fscanf(f, "%u %u", &a, &b) == 2) {
+    uint32_t p, q;
+    if (!net_.id2seq(a, &p) || !net_.id2seq(b, &q)) {
+      fprintf(stderr, "error: id %d or id %d not found in original network\n", a, b);
+      exit(-1);
+    }
+    Edge e(p, q);
+    Network::order_edge(e);
+    validation_pairs_.push_back(e);
+    ++cnt;
+    int c;   // the reference's pattern is "%d\t%d\n": a third column (y) on the line is not expected
+    while ((c = fgetc(f)) != EOF && c != '\n') {}
+  }
+  fclose(f);
+  validation_sorted_ = validation_pairs_;
+  std::sort(validation_sorted_.begin(), validation_sorted_.end());
+  validation_sorted_.erase(std::unique(validation_sorted_.begin(), validation_sorted_.end()), validation_sorted_.end());
+  env_.plog("link sampling: loaded validation heldout pairs:", cnt);
+}
+
+void LinkSampling::init_gamma2() {
+  std::vector<double> phi(k_);
+  for (uint32_t p = 0; p < n_; ++p)
+    for (uint32_t q : net_.get_edges(p)) {
+      if (p >= q) continue;
+      for (uint32_t c = 0; c < k_; ++c) phi[c] = rng_.uniform();
+      double s = .0;
+      for (uint32_t c = 0; c < k_; ++c) s += phi[c];
+      for (uint32_t c = 0; c < k_; ++c) phi[c] = phi[c] / s;
+      double *gp = &gamma_[(size_t)p * k_], *gq = &gamma_[(size_t)q * k_];
+      for (uint32_t c = 0; c < k_; ++c) gp[c] += phi[c];
+      for (uint32_t c = 0; c < k_; ++c) gq[c] += phi[c];
+    }
+}
+
+int LinkSampling::load_model() {
+  // <dir>gamma.txt: "seq \t id \t g_0 .. g_K-1"; <dir>lambda.txt: "k \t l_0 \t l_1"  (Appendix C)
+  const std::string gpath = env_.gamma_location + "gamma.txt", lpath = env_.gamma_location + "lambda.txt";
+  FILE *gf = fopen(gpath.c_str(), "r");
+  if (!gf) { fprintf(stderr, "no gamma.txt found\n"); return -1; }
+  std::vector<char> line(32 * (size_t)k_ + 64);
+  uint32_t rows = 0;
+  while (fgets(line.data(), (int)line.size(), gf)) {
+    char *p = line.data();
+    uint32_t col = 0;
+    for (;;) {
+      char *q = nullptr;
+      const double d = strtod(p, &q);
+      if (q == p) break;
+      p = q;
+      if (col >= 2 && col - 2 < k_ && rows < n_) gamma_[(size_t)rows * k_ + col - 2] = d;
+      col++;
+    }
+    if (col < k_ + 1) { fprintf(stderr, "error parsing gamma file\n"); return -1; }
+    rows++;
+  }
+  fclose(gf);
+  if (rows != n_) { fprintf(stderr, "gamma.txt has %u rows, expected %u\n", rows, n_); return -1; }
+  FILE *lf = fopen(lpath.c_str(), "r");
+  if (!lf) { fprintf(stderr, "no lambda.txt found\n"); return -1; }
+  rows = 0;
+  while (fgets(line.data(), (int)line.size(), lf)) {
+    char *p = line.data();
+    uint32_t col = 0;
+    for (;;) {
+      char *q = nullptr;
+      const double d = strtod(p, &q);
+      if (q == p) break;
+      p = q;
+      if (col >= 1 && col - 1 < 2 && rows < k_) lambda_[(size_t)rows * 2 + col - 1] = d;
+      col++;
+    }
+    rows++;
+  }
+  fclose(lf);
+  if (rows != k_) { fprintf(stderr, "lambda.txt has %u rows, expected %u\n", rows, k_); return -1; }
+  return 0;
+}
+
+void LinkSampling::assign_training_links() {
+  training_links_.assign(n_, 0.0);
+  links_.clear();
+  for (uint32_t p = 0; p < n_; ++p)
+    for (uint32_t q : net_.get_edges(p)) {
+      if (!env_.accuracy) {
+        Edge e(p, q);
+        Network::order_edge(e);
+        if (!edge_ok(e)) continue;   // held out
+      }
+      training_links_[p]++;          // both adjacency directions count: tl = 2 x degree
+      training_links_[q]++;
+      if (p >= q) continue;
+      links_.push_back(p);
+      links_.push_back(q);
+    }
+}
+
+bool LinkSampling::validation_likelihood() {
+  if (env_.accuracy) return false;
+  DEV(svi_ls_heldout(dev_, hp_.size(), hp_.data(), hq_.data(), hy_.data(), env_.epsilon, hll_.data()));
+  uint32_t k = 0, kzeros = 0, kones = 0;
+  double s = .0, szeros = 0, sones = 0;
+  for (size_t i = 0; i < hll_.size(); ++i) {
+    const double u = hll_[i];
+    s += u;
+    k += 1;
+    if (hy_[i]) { sones += u; kones++; } else { szeros += u; kzeros++; }
+  }
+  const double nshol = (zeros_prob_ * (szeros / kzeros)) + (ones_prob_ * (sones / kones));
+  fprintf(vf_, "%d\t%d\t%.9f\t%d\t%.9f\t%d\t%.9f\t%d\t%.9f\t%.9f\t%.9f\n", iter_, duration(), s / k, k,
+          szeros / kzeros, kzeros, sones / kones, kones, zeros_prob_ * (szeros / kzeros),
+          ones_prob_ * (sones / kones), nshol);
+  fflush(vf_);
+
+  // stop state machine, :1006-1049
+  const double a = nshol;
+  bool stop = false;
+  int why = -1;
+  if (iter_ > 10) {
+    if (a > prev_h_ && prev_h_ != 0 && fabs((a - prev_h_) / prev_h_) < 0.00001) {
+      stop = true;
+      why = 100;
+    } else if (a < prev_h_) {
+      nh_++;
+    } else if (a > prev_h_) {
+      nh_ = 0;
+    }
+    if (a > max_h_) { max_h_ = a; max_t_ = 0; }
+    if (nh_ > 2) { why = 1; stop = true; }
+  }
+  prev_h_ = nshol;
+  if (FILE *f = fopen(env_.file("/max.txt").c_str(), "w")) {
+    fprintf(f, "%d\t%d\t%.5f\t%.5f\t%.5f\t%d\n", iter_, duration(), a, max_t_, max_h_, why);
+    fclose(f);
+  }
+  if (annealing_ && stop) {        // the first "stop" only ends the annealing phase
+    annealing_ = false;
+    nh_ = 0;
+    prev_h_ = 0;
+    return false;
+  }
+  return stop && env_.use_validation_stop;
+}
+
+void LinkSampling::test_likelihood_line() {
+  if (env_.accuracy) return;
+  // the reference evaluates its (empty) test map every report and logs the resulting 0/0 (Q11)
+  const double nan = std::nan("");
+  fprintf(tf_, "%d\t%d\t%.9f\t%d\t%.9f\t%d\t%.9f\t%d\t%.9f\t%.9f\t%.9f\n", iter_, duration(), -nan, 0, -nan, 0, -nan, 0,
+          -nan, -nan, -nan);
+  fflush(tf_);
+}
+
+void LinkSampling::fetch_state() { DEV(svi_ls_get_state(dev_, gamma_.data(), lambda_.data())); }
+
+void LinkSampling::save_model() {
+  FILE *gf = open_or_die(env_.file("/gamma.txt"), "w", "gamma");
+  const uint32_t k = k_;
+  write_rows(gf, n_, [&](uint32_t i, std::string &s) {
+    char b[48];
+    s.append(b, (size_t)snprintf(b, sizeof b, "%d\t%d\t", i, net_.seq2id(i)));
+    const double *g = &gamma_[(size_t)i * k];
+    for (uint32_t c = 0; c < k; ++c) append_fmt(s, c == k - 1 ? "%.5f\n" : "%.5f\t", g[c]);
+  });
+  fclose(gf);
+  FILE *lf = open_or_die(env_.file("/lambda.txt"), "w", "lambda");
+  for (uint32_t c = 0; c < k_; ++c) fprintf(lf, "%d\t%.5f\t%.5f\n", c, lambda_[2 * c], lambda_[2 * c + 1]);
+  fclose(lf);
+}
+
+void LinkSampling::write_groups() {
+  FILE *f = open_or_die(env_.file("/groups.txt"), "w", "groups");
+  const uint32_t k = k_;
+  write_rows(f, n_, [&](uint32_t i, std::string &s) {
+    char b[48];
+    s.append(b, (size_t)snprintf(b, sizeof b, "%d\t%d\t", i, net_.seq2id(i)));
+    const double *g = &gamma_[(size_t)i * k];
+    double sum = .0;
+    for (uint32_t c = 0; c < k; ++c) sum += g[c];
+    for (uint32_t c = 0; c < k; ++c) append_fmt(s, c == k - 1 ? "%.3f\n" : "%.3f\t", g[c] / sum);
+  });
+  fclose(f);
+}
+
+void LinkSampling::write_communities(const std::string &name) {
+  // one line per non-empty link community, ascending k: external ids ascending, each followed by ' '
+  const uint32_t words = (k_ + 31) / 32;
+  if (member_bits_.size() != (size_t)n_ * words) member_bits_.assign((size_t)n_ * words, 0);
+  if (have_membership_) DEV(svi_ls_get_membership(dev_, member_bits_.data()));
+  std::vector<std::vector<uint32_t>> comm(k_);
+  for (uint32_t p = 0; p < n_; ++p)
+    for (uint32_t w = 0; w < words; ++w) {
+      uint32_t bits = member_bits_[(size_t)p * words + w];
+      while (bits) {
+        const uint32_t c = w * 32 + (uint32_t)__builtin_ctz(bits);
+        bits &= bits - 1;
+        if (c < k_) comm[c].push_back(net_.seq2id(p));
+      }
+    }
+  FILE *f = open_or_die(env_.file(name), "w", "communities");
+  std::string line;
+  for (uint32_t c = 0; c < k_; ++c) {
+    if (comm[c].empty()) continue;
+    std::sort(comm[c].begin(), comm[c].end());
+    line.clear();
+    char b[16];
+    for (uint32_t id : comm[c]) line.append(b, (size_t)snprintf(b, sizeof b, "%d ", id));
+    line.push_back('\n');
+    fwrite(line.data(), 1, line.size(), f);
+  }
+  fclose(f);
+}
+
+void LinkSampling::log_communities() {
+  write_communities("/communities.txt");
+  if (env_.nmi) fprintf(stderr, "svinet: -nmi needs the external `mutual` binary and is skipped in this build\n");
+}
+
+void LinkSampling::do_on_stop() {
+  log_communities();
+  fetch_state();
+  save_model();
+  write_groups();
+}
+
+void LinkSampling::infer() {
+  bool write_comm = false;
+  const uint32_t rf = (uint32_t)env_.reportfreq;
+  while (1) {
+    if (env_.max_iterations && iter_ > env_.max_iterations) {
+      printf("+ Quitting: reached max iterations.\n");
+      env_.plog("maxiterations reached", true);
+      env_.terminate = true;
+      do_on_stop();
+      exit(0);
+    }
+    if (env_.max_iterations == 1) write_comm = true;
+    printf("\riteration %d: processing %zu links", iter_, links_.size() / 2);
+    fflush(stdout);
+    DEV(svi_ls_step(dev_, iter_, annealing_ ? 1 : 0, write_comm ? 1 : 0));
+    if (write_comm) have_membership_ = true;
+
+    if (env_.terminate) {             // SIGTERM: dump the model and carry on (:763-766)
+      do_on_stop();
+      env_.terminate = false;
+    }
+    write_comm = (iter_ % rf == rf - 1);
+    if (iter_ % rf == 0) {
+      if (validation_likelihood()) {
+        do_on_stop();
+        exit(0);
+      }
+      test_likelihood_line();
+      log_communities();
+    }
+    iter_++;
+  }
+}
+
+void LinkSampling::dump_init(const std::string &dir) const {
+  auto dump = [&](const char *name, const void *p, size_t bytes) {
+    FILE *f = open_or_die(dir + "/" + name, "wb", name);
+    if (bytes) fwrite(p, 1, bytes, f);
+    fclose(f);
+  };
+  std::vector<uint32_t> vp;
+  for (const Edge &e : validation_pairs_) { vp.push_back(e.first); vp.push_back(e.second); }
+  dump("gamma.f64", gamma_.data(), gamma_.size() * sizeof(double));
+  dump("lambda.f64", lambda_.data(), lambda_.size() * sizeof(double));
+  dump("validation.u32", vp.data(), vp.size() * sizeof(uint32_t));
+  dump("links.u32", links_.data(), links_.size() * sizeof(uint32_t));
+  dump("tl.f64", training_links_.data(), training_links_.size() * sizeof(double));
+}

@@ -1,0 +1,79 @@
+// linksampling.hh -- the drop-in `LinkSampling` of the svinet CLI, B200 build.
+//
+// Same seam as the reference class used at src/main.cc:337-341:
+//     LinkSampling ls(env, network);  ls.infer();          // infer() ends the process with exit(0)
+// The constructor keeps every host responsibility of the reference's (src/linksampling.cc:5-155): RNG,
+// held-out draw, gamma/lambda initialisation, output files.  infer() (src/linksampling.cc:557-790)
+// hands the whole loop body to the device through the C ABI in include/svi_ls.h and keeps the stop
+// state machine, the SIGTERM poll and the file writers on the host.
+#ifndef SVINET_B200_LINKSAMPLING_HH
+#define SVINET_B200_LINKSAMPLING_HH
+
+#include <cstdint>
+#include <cstdio>
+#include <ctime>
+#include <string>
+#include <vector>
+
+#include "env.hh"
+#include "network.hh"
+#include "rng.hh"
+#include "svi_ls.h"
+
+class LinkSampling {
+ public:
+  LinkSampling(Env &env, Network &network);
+  ~LinkSampling();
+
+  void infer();        // never returns normally (exit(0) on stop / max-iterations), like the reference
+  void save_model();   // gamma.txt + lambda.txt (src/linksampling.cc:805-837)
+
+  // test hook (not in the reference): dump the initial state instead of running, see main.cc -dump-init
+  void dump_init(const std::string &dir) const;
+
+ private:
+  // --- start-up, host side ---
+  void init_validation();                 // :165-188
+  void load_validation();                 // :1383-1414
+  void set_validation_sample(int s);      // :281-309
+  void get_random_edge(bool link, Edge &e);   // src/linksampling.hh:328-349
+  bool edge_ok(const Edge &e) const;      // src/linksampling.hh:296-326
+  void init_gamma2();                     // :374-401
+  int load_model();                       // :1266-1352
+  void assign_training_links();           // :493-523
+  // --- per report ---
+  bool validation_likelihood();           // :966-1050, true = the run must end
+  void test_likelihood_line();            // :1147-1182 on the (always empty) test set
+  void log_communities();                 // :839-852
+  void write_communities(const std::string &name);   // :882-917
+  void write_groups();                    // :1452-1476
+  void do_on_stop();                      // :792-802
+  void fetch_state();                     // device -> gamma_/lambda_
+  uint32_t duration() const { return (uint32_t)(time(0) - start_time_); }
+
+  Env &env_;
+  Network &net_;
+  uint32_t n_, k_;
+  uint32_t iter_ = 0;                     // the reference never initialises it; observed 0
+  double total_pairs_ = 0, ones_prob_ = 0, zeros_prob_ = 0;
+  Mt19937 rng_;
+  std::vector<double> gamma_, lambda_;    // host mirrors (n*k, k*2)
+  std::vector<Edge> validation_pairs_;    // draw order
+  std::vector<Edge> validation_sorted_;   // std::map<Edge,bool> iteration order
+  std::vector<uint32_t> links_;           // training links (p<q), reference order
+  std::vector<double> training_links_;    // tl[p] = 2 x training degree
+  std::vector<uint32_t> member_bits_;     // last write_comm tally fetched from the device
+  bool have_membership_ = false;
+  bool annealing_ = true;
+  double max_t_ = -2147483647, max_h_ = -2147483647, prev_h_ = -2147483647;
+  uint32_t nh_ = 0;
+  time_t start_time_;
+  FILE *vf_ = nullptr, *tf_ = nullptr, *lf_ = nullptr;
+  svi_ls *dev_ = nullptr;
+  // held-out pairs in evaluation order, flattened for svi_ls_heldout
+  std::vector<uint32_t> hp_, hq_;
+  std::vector<uint8_t> hy_;
+  std::vector<double> hll_;
+};
+
+#endif

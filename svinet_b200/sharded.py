@@ -1,0 +1,183 @@
+"""Node-block sharding of the link-sampling iteration across the GPUs of one box.
+
+One process per GPU (torchrun), torch.distributed for the plumbing.  Rank r owns a contiguous block of
+nodes chosen so that every rank sweeps about the same number of half-edges; it holds the CSR of the
+half-edges whose SOURCE is in its block (pull form: a link is processed by both endpoint owners, each
+updating only its own row, so there is no cross-GPU scatter), the full N x K factor / mean-indicator
+matrices (neighbour rows can live anywhere), and refreshes only its own rows.  Per iteration the path
+has three real exchange steps, done with NCCL over NVLink/NVSwitch:
+
+    phase_phi ; phase_node
+        all-reduce   sum, s1, s2            (3 K-vectors; `sum` feeds the annealing rescale, :541-542)
+        all-gather   mphi rows              (N x K doubles in total)
+    phase_s3
+        all-reduce   s3                     (1 K-vector)
+    phase_finish
+        all-gather   exp(Elogpi) rows, converged[]   (+ active masks once iter > 1000)
+
+The row all-gathers are the only bulk traffic: 2 x N*K*8 bytes per iteration (3.2 GB at n=1M, k=200)
+against ~480 GB of local HBM traffic divided by the number of GPUs.
+
+The collective choreography is independent of what executes the phases: `engine_factory` lets the CPU
+tests (gloo, world_size 2) drive it with a numpy stand-in; the product path builds the CUDA engine and
+refuses to run without a GPU.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def plan_shards(n, links, world):
+    """Edge-balanced contiguous node blocks: boundaries[r] .. boundaries[r+1] holds ~1/world of the
+    half-edges (every link contributes one half-edge to each endpoint)."""
+    links = np.asarray(links).reshape(-1, 2)
+    deg = np.bincount(links.ravel().astype(np.int64), minlength=n).astype(np.int64)
+    csum = np.concatenate([[0], np.cumsum(deg)])
+    total = csum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r // world
+        b = int(np.searchsorted(csum, target, side="left"))
+        bounds.append(min(max(b, bounds[-1]), n))
+    bounds.append(n)
+    return np.asarray(bounds, dtype=np.int64)
+
+
+class _DevArray:
+    """Zero-copy torch view of a device buffer owned by the C library (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr,
+                                         "version": 2, "strides": None}
+
+
+def cuda_view(ptr, shape, dtype, device):
+    typestr = {torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
+
+
+class CudaShardEngine:
+    """The product engine for one shard: libsvi_ls.so through svinet_b200.engine (CUDA only)."""
+
+    def __init__(self, n, k, links, node_range, device, stream, **kw):
+        if not torch.cuda.is_available():
+            raise RuntimeError("svinet_b200.sharded: no CUDA device; the product path has no CPU fallback")
+        from .engine import LinkSamplingEngine
+        self.eng = LinkSamplingEngine(n, k, links, device=device, node_range=node_range, stream=stream, **kw)
+        self.n, self.k = n, k
+        self.device = torch.device("cuda", device)
+        self.ld = self.eng.info()["ld"]
+        self.words = (k + 31) // 32
+
+    def buffer(self, name):
+        ptr, ld = self.eng.device_buffer(name)
+        if name in ("exppi", "mphi", "gamma"):
+            return cuda_view(ptr, (self.n, self.ld), torch.float64, self.device)
+        if name == "kvec":
+            return cuda_view(ptr, (4, self.ld), torch.float64, self.device)
+        if name in ("converged", "active"):
+            return cuda_view(ptr, (self.n,), torch.int32, self.device)
+        if name in ("active_bits", "member_bits"):
+            return cuda_view(ptr, (self.n, self.words), torch.int32, self.device)
+        raise KeyError(name)
+
+    def __getattr__(self, item):          # phase_phi, phase_node, phase_s3, phase_finish, set_state, ...
+        return getattr(self.eng, item)
+
+
+class ShardedLinkSampling:
+    def __init__(self, n, k, links, rank, world, device=0, stream=None, engine_factory=None, group=None, **kw):
+        self.n, self.k, self.rank, self.world, self.group = n, k, rank, world, group
+        links = np.ascontiguousarray(links, dtype=np.uint32).reshape(-1, 2)
+        self.bounds = plan_shards(n, links, world)
+        nb, ne = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        # only the links incident to this block are needed to build the shard's CSR; tl (2 x degree) is a
+        # whole-graph quantity and is passed explicitly
+        tl = 2.0 * np.bincount(links.ravel().astype(np.int64), minlength=n).astype(np.float64)
+        mine = ((links[:, 0] >= nb) & (links[:, 0] < ne)) | ((links[:, 1] >= nb) & (links[:, 1] < ne))
+        factory = engine_factory or CudaShardEngine
+        self.eng = factory(n, k, links[mine], (nb, ne), device, stream, tl=tl, ones=links.shape[0], **kw)
+        self.nlinks = links.shape[0]
+        self.local_half_edges = int(tl[nb:ne].sum() // 2)
+        self._buf = {name: self.eng.buffer(name) for name in
+                     ("exppi", "mphi", "gamma", "kvec", "converged", "active", "active_bits", "member_bits")}
+
+    # ---- collectives on the engine's own buffers ----
+    def _allreduce(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _allgather_rows(self, name):
+        """Every rank broadcasts its own row block of the (replicated-layout) buffer `name`."""
+        buf = self._buf[name]
+        for r in range(self.world):
+            b, e = int(self.bounds[r]), int(self.bounds[r + 1])
+            if e > b:
+                dist.broadcast(buf[b:e], src=r, group=self.group)
+
+    def set_state(self, gamma, lam):
+        self.eng.set_state(gamma, lam)     # derives the factors of ALL rows, no exchange needed
+
+    def step(self, it, annealing, write_comm, events=None, stream=None):
+        def mark(i):
+            if events is not None:
+                events[i].record(stream) if stream is not None else events[i].record()
+        kv = self._buf["kvec"]
+        self.eng.phase_phi(it, write_comm)
+        mark(1)
+        self.eng.phase_node()
+        self._allreduce(kv[0:3])
+        self._allgather_rows("mphi")
+        mark(2)
+        self.eng.phase_s3()
+        self._allreduce(kv[3:4])
+        mark(3)
+        self.eng.phase_finish(annealing)
+        self._allgather_rows("exppi")
+        self._allgather_rows("converged")
+        if it >= 1000:                     # the active-set branch reads neighbours' masks (:634)
+            self._allgather_rows("active")
+            self._allgather_rows("active_bits")
+
+    def gather_state(self):
+        """Full gamma [n,k] and lambda [k,2] on every rank (for save_model / parity checks)."""
+        self._allgather_rows("gamma")
+        return self.eng.get_state()
+
+    def gather_membership(self):
+        self._allgather_rows("member_bits")
+        return self.eng.membership()
+
+    def phase_ms(self, ev):
+        import numpy as _np
+        return [float(_np.mean([e[i].elapsed_time(e[i + 1]) for e in ev])) for i in range(4)]
+
+    def e2e(self, step_fn, it0, steps, nlinks, unit):
+        """Same step driven with HOST state: every step each rank uploads the full gamma/lambda from pinned
+        memory (svi_ls_set_state), runs the sharded iteration, and downloads gamma/lambda
+        (svi_ls_get_state after the row all-gather)."""
+        import time
+        n, k = self.n, self.k
+        pin_g = torch.empty((n, k), dtype=torch.float64).pin_memory()
+        pin_l = torch.empty((k, 2), dtype=torch.float64).pin_memory()
+        self._allgather_rows("gamma")
+        self.eng.get_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
+        it = it0
+        for timed in (False, True):
+            dist.barrier(group=self.group)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(1 if not timed else steps):
+                self.eng.set_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
+                step_fn(it)
+                it += 1
+                self._allgather_rows("gamma")
+                self.eng.get_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        state_bytes = (n * k + 2 * k) * 8
+        return {"value": nlinks * steps / float(t.item()), "unit": unit, "steps": steps,
+                "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
+                "what": "per rank: svi_ls_set_state(pinned host) + sharded step (NCCL exchanges) + gamma row "
+                        "all-gather + svi_ls_get_state(pinned host); bytes are per rank"}

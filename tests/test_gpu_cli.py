@@ -1,0 +1,72 @@
+"""End-to-end drop-in check on a B200: the C++ CLI (svinet_b200/lib/svinet) is run with the same flags the
+UNMODIFIED reference was run with when tests/golden/ was generated, in a scratch cwd, and its output
+directory is compared file by file with the reference's: communities.txt and validation-edges.txt
+byte-for-byte, the numeric files field by field with +-1 unit of the last printed digit (SURVEY.md
+Appendix F), wall-clock columns excluded."""
+import os
+import subprocess
+
+import pytest
+
+from golden_util import MANIFEST, Scratch, compare_numeric_text, golden_text, input_path
+from svinet_b200 import build as svbuild
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cli():
+    svbuild.build_lib()
+    path = svbuild.build_cli()
+    assert path and os.path.exists(path)
+    return path
+
+
+def run_case(cli, case, d):
+    ent = MANIFEST[case]
+    inp = input_path(ent["input"], d)
+    local = os.path.join(d, ent["input"])
+    if not os.path.exists(local):
+        os.symlink(inp, local)
+    cmd = [cli, "-file", ent["input"], "-n", str(ent["n"]), "-k", str(ent["k"]), "-link-sampling"] + ent["flags"]
+    p = subprocess.run(cmd, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=600)
+    assert p.returncode == 0, p.stderr.decode()
+    return ent, os.path.join(d, ent["outdir"])
+
+
+@pytest.mark.parametrize("case", ["c1_m30", "c1_natural", "c1_m1", "c1_seed7_m12", "c1_accuracy_m8", "c1_k7_m15",
+                                  "lfr_k28_m20", "c2_m12", "c2_m25"])
+def test_cli_output_directory_matches_reference(cli, case):
+    with Scratch() as d:
+        ent, out = run_case(cli, case, d)
+        flips = {}
+        for fname in ("gamma.txt", "lambda.txt", "groups.txt", "validation.txt", "max.txt"):
+            want = golden_text(case, fname)
+            if want is None:
+                continue
+            got = open(os.path.join(out, fname)).read()
+            flips[fname] = compare_numeric_text(got, want, skip_cols=(1,) if fname in ("validation.txt", "max.txt") else ())
+        for fname in ("communities.txt", "validation-edges.txt", "param.txt"):
+            want = golden_text(case, fname)
+            if want is not None:
+                assert open(os.path.join(out, fname)).read() == want, fname
+        nf, noff = flips["gamma.txt"]
+        assert noff <= max(2, nf // 10000), flips      # a handful of last-digit roundings at most
+        for f in ("infer.log", "logl.txt", "test-edges.txt", "network.dat"):
+            assert os.path.lexists(os.path.join(out, f)), f
+
+
+def test_cli_resume_from_saved_model(cli):
+    """-load <dir/> (checkpoint/resume, linksampling.cc:1267-1352): a run resumed from a saved model's %.5f
+    text starts from exactly that gamma/lambda."""
+    with Scratch() as d:
+        ent, out = run_case(cli, "c1_m30", d)
+        os.rename(out, os.path.join(d, "saved"))
+        cmd = [cli, "-file", ent["input"], "-n", "75", "-k", "4", "-link-sampling", "-load", "saved/", "-label", "resumed",
+               "-dump-init", d]
+        subprocess.check_call(cmd, cwd=d, stdout=subprocess.DEVNULL)
+        import numpy as np
+        gam = np.fromfile(os.path.join(d, "gamma.f64")).reshape(75, 4)
+        want = np.array([[float(x) for x in l.split("\t")[2:]] for l in
+                         open(os.path.join(d, "saved", "gamma.txt")).read().strip().split("\n")])
+        assert np.array_equal(gam, want)

@@ -1,0 +1,117 @@
+"""Host-side logic of the C++ drop-in CLI (svinet_b200/host) without a GPU.
+
+`svinet ... -dump-init DIR` runs everything the reference's constructor does on the host -- ingest,
+id mapping, MT19937 held-out draw, init_gamma2, training-link assignment, param.txt -- writes the result
+as raw arrays and exits before the first device call.  Integer/RNG work must match the oracle (and,
+through it, the reference) bit for bit."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_py as orc
+from golden_util import MANIFEST, Scratch, golden_text, input_path
+from svinet_b200 import build as svbuild
+
+
+@pytest.fixture(scope="module")
+def cli():
+    svbuild.build_lib()
+    path = svbuild.build_cli()
+    assert path and os.path.exists(path)
+    return path
+
+
+def run_dump(cli, case, d, extra=()):
+    ent = MANIFEST[case]
+    inp = input_path(ent["input"], d)
+    local = os.path.join(d, ent["input"])
+    if not os.path.exists(local):
+        os.symlink(inp, local)
+    dump = os.path.join(d, "dump")
+    os.makedirs(dump, exist_ok=True)
+    cmd = [cli, "-file", ent["input"], "-n", str(ent["n"]), "-k", str(ent["k"]), "-link-sampling"] + ent["flags"] + \
+          list(extra) + ["-dump-init", dump]
+    subprocess.check_call(cmd, cwd=d, stdout=subprocess.DEVNULL)
+    k = ent["k"]
+    out = {
+        "gamma": np.fromfile(os.path.join(dump, "gamma.f64")).reshape(-1, k),
+        "lambda": np.fromfile(os.path.join(dump, "lambda.f64")).reshape(k, 2),
+        "validation": np.fromfile(os.path.join(dump, "validation.u32"), dtype=np.uint32).reshape(-1, 2),
+        "links": np.fromfile(os.path.join(dump, "links.u32"), dtype=np.uint32).reshape(-1, 2),
+        "tl": np.fromfile(os.path.join(dump, "tl.f64")),
+        "outdir": os.path.join(d, ent["outdir"]),
+    }
+    return ent, out
+
+
+def oracle_opts(flags):
+    o = {}
+    if "-seed" in flags:
+        o["seed"] = float(flags[flags.index("-seed") + 1])
+    if "-accuracy" in flags:
+        o["accuracy"] = 1
+    return o
+
+
+@pytest.mark.parametrize("case", ["c1_m30", "c1_seed7_m12", "c1_accuracy_m8", "c1_k7_m15", "lfr_k28_m20"])
+def test_startup_state_is_bit_identical_to_oracle(cli, case):
+    with Scratch() as d:
+        ent, got = run_dump(cli, case, d)
+        g = orc.Graph.read(input_path(ent["input"], d), ent["n"])
+        m = orc.Model(g, ent["k"], **oracle_opts(ent["flags"]))
+        st = m.state
+        assert np.array_equal(got["gamma"], st.arr("gamma"))            # same RNG stream, same order
+        assert np.array_equal(got["lambda"], st.arr("lambda_"))
+        assert np.array_equal(got["validation"], m.validation_pairs())
+        assert np.array_equal(got["links"], st.arr("links"))
+        assert np.array_equal(got["tl"], st.arr("tl"))
+        # files the constructor writes: identical to what the REFERENCE wrote for the same flags
+        assert open(os.path.join(got["outdir"], "validation-edges.txt")).read() == \
+            golden_text(case, "validation-edges.txt")
+        want = golden_text(case, "param.txt").split("\n")
+        have = open(os.path.join(got["outdir"], "param.txt")).read().split("\n")
+        have = [l for l in have if l]
+        assert have == want[:len(have)] and len(have) >= 50
+        assert os.path.islink(os.path.join(got["outdir"], "network.dat"))
+        m.close(); g.close()
+
+
+def test_astroph_ingest_matches_oracle(cli):
+    with Scratch() as d:
+        ent, got = run_dump(cli, "c2_m12", d)
+        g = orc.Graph.read(input_path(ent["input"], d), ent["n"])
+        m = orc.Model(g, ent["k"])
+        assert got["links"].shape == (195988, 2)                        # training links of config 2
+        assert np.array_equal(got["links"], m.state.arr("links"))
+        assert np.array_equal(got["gamma"], m.state.arr("gamma"))
+        assert np.array_equal(got["validation"], m.validation_pairs())
+        m.close(); g.close()
+
+
+def test_ragged_input_selfloops_duplicates_and_single_nodes(cli):
+    """Self-loops and repeated / reversed pairs are dropped, ids are arbitrary integers, and -n larger than
+    the number of distinct ids pads the graph with 'single' nodes (network.cc:107-113) that inference skips."""
+    with Scratch() as d:
+        lines = ["10\t20", "20\t10", "10\t10", "30\t20", "10\t20", "7\t30", "7\t10", "99\t99", "5\t7"]
+        open(os.path.join(d, "g.txt"), "w").write("\n".join(lines) + "\n")
+        dump = os.path.join(d, "dump"); os.makedirs(dump)
+        subprocess.check_call([cli, "-file", "g.txt", "-n", "9", "-k", "3", "-link-sampling", "-accuracy",
+                               "-dump-init", dump], cwd=d, stdout=subprocess.DEVNULL)
+        links = np.fromfile(os.path.join(dump, "links.u32"), dtype=np.uint32).reshape(-1, 2)
+        gamma = np.fromfile(os.path.join(dump, "gamma.f64")).reshape(-1, 3)
+        g = orc.Graph.read(os.path.join(d, "g.txt"), 9)
+        assert (g.n, g.singles, g.ones) == (6, 3, 5)
+        m = orc.Model(g, 3, accuracy=1)
+        assert gamma.shape == (6, 3)
+        assert np.array_equal(links, m.state.arr("links")) and np.array_equal(gamma, m.state.arr("gamma"))
+        # node 99 only has a self-loop: it exists, has no links and an all-zero initial gamma row
+        assert np.all(gamma[4] == 0)                                    # ids in first-appearance order: 99 -> seq 4
+        m.close(); g.close()
+
+
+def test_cli_refuses_other_engines(cli):
+    with Scratch() as d:
+        p = subprocess.run([cli, "-file", "x", "-n", "5", "-k", "2", "-batch"], cwd=d, capture_output=True)
+        assert p.returncode != 0 and b"only -link-sampling" in p.stderr
