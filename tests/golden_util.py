@@ -1,5 +1,6 @@
 """Helpers shared by the golden-vector tests (test infrastructure)."""
 import gzip
+from decimal import Decimal
 import json
 import os
 import shutil
@@ -49,8 +50,9 @@ def compare_numeric_text(got, want, ulp_last_digit=1, skip_cols=()):
                 continue
             if "." in y and "nan" not in y and "inf" not in y:
                 decimals = len(y.split(".")[1])
-                tol = ulp_last_digit * 10.0 ** (-decimals) * 1.0000001
-                assert abs(float(x) - float(y)) <= tol, "line %d col %d: %s vs %s" % (ln, col, x, y)
+                # exact decimal arithmetic on the printed digits (binary floats cannot represent 1e-5 steps)
+                diff = abs(Decimal(x) - Decimal(y)).scaleb(decimals)
+                assert diff <= ulp_last_digit, "line %d col %d: %s vs %s" % (ln, col, x, y)
                 noff += 1
             else:
                 raise AssertionError("line %d col %d: %s vs %s" % (ln, col, x, y))
