@@ -6,7 +6,8 @@ TEST INFRASTRUCTURE ONLY.  Run in the build container (needs oracle/_ref, i.e.
 
     python oracle/make_golden.py
 
-Each case runs `svinet_ref -file G -n N -k K -link-sampling <flags>` in a scratch
+Each case runs `svinet_ref -file G -n N -k K -link-sampling <flags>` (or `-rnode -stratified <flags>` for
+the fa2_* cases, class FastAMM2) in a scratch
 directory (the reference writes its output directory into the cwd, env.hh:503-568) and
 copies the files that pin the path's results into tests/golden/<case>/.  The wall-clock
 "secs" column (col 2 of validation.txt / max.txt, linksampling.cc:996-1002,1030-1034) is
@@ -43,6 +44,19 @@ CASES = {
     "c2_m25": ("ca-AstroPh.csv", 17903, 20, ["-max-iterations", "25", "-no-stop"], "n17903-k20-mmsb-linksampling"),
 }
 
+# `-rnode -stratified` (class FastAMM2): name -> (input, n, k, flags, outdir)
+FA2_CASES = {
+    "fa2_c1_m200": ("assort-75-4.txt", 75, 4, ["-max-iterations", "200", "-rfreq", "50"], "n75-k4-mmsb-Srnode"),
+    "fa2_c1_k6_seed9_m500": ("assort-75-4.txt", 75, 6, ["-max-iterations", "500", "-rfreq", "100", "-seed", "9"],
+                             "n75-k6-mmsb-seed9-Srnode"),
+    "fa2_lfr_k28_m300": ("LFR-network-n1000-k28.txt", 1000, 28, ["-max-iterations", "300", "-rfreq", "100"],
+                         "n1000-k28-mmsb-Srnode"),
+    "fa2_c2_m120": ("ca-AstroPh.csv", 17903, 20, ["-max-iterations", "120", "-rfreq", "40"],
+                    "n17903-k20-mmsb-Srnode"),
+}
+FA2_KEEP = ["gamma.txt", "lambda.txt", "heldout.txt", "heldout-pairs.txt", "groups.txt", "communities.txt",
+            "communities_size.txt", "summary.txt", "param.txt"]
+
 KEEP = ["gamma.txt", "lambda.txt", "communities.txt", "groups.txt", "validation.txt", "max.txt",
         "validation-edges.txt", "param.txt"]
 GZIP_OVER = 256 * 1024
@@ -66,12 +80,14 @@ def main():
     only = set(sys.argv[1:])
     manifest_path = os.path.join(GOLD, "MANIFEST.json")
     manifest = json.load(open(manifest_path)) if os.path.exists(manifest_path) else {}
-    for name, (fname, n, k, flags, outdir) in CASES.items():
+    jobs = [(name, c, "-link-sampling", KEEP) for name, c in CASES.items()]
+    jobs += [(name, c, "-rnode -stratified", FA2_KEEP) for name, c in FA2_CASES.items()]
+    for name, (fname, n, k, flags, outdir), mode, keep in jobs:
         if only and name not in only:
             continue
         scratch = tempfile.mkdtemp(prefix="golden_")
         shutil.copy(os.path.join(DATA, fname), os.path.join(scratch, fname))
-        cmd = [REF_BIN, "-file", fname, "-n", str(n), "-k", str(k), "-link-sampling"] + flags
+        cmd = [REF_BIN, "-file", fname, "-n", str(n), "-k", str(k)] + mode.split() + flags
         with open(os.path.join(scratch, "stdout.log"), "w") as log:
             rc = subprocess.call(cmd, cwd=scratch, stdout=log, stderr=subprocess.STDOUT)
         if rc != 0:
@@ -80,12 +96,12 @@ def main():
         dst = os.path.join(GOLD, name)
         shutil.rmtree(dst, ignore_errors=True)
         os.makedirs(dst)
-        entry = {"input": fname, "n": n, "k": k, "flags": flags, "outdir": outdir, "md5": {}}
-        for f in KEEP:
+        entry = {"input": fname, "n": n, "k": k, "flags": flags, "outdir": outdir, "md5": {}, "mode": mode}
+        for f in keep:
             p = os.path.join(src, f)
             if not os.path.exists(p):
                 continue
-            if f in ("validation.txt", "max.txt"):
+            if f in ("validation.txt", "max.txt", "heldout.txt"):
                 zero_secs_column(p)
             data = open(p, "rb").read()
             entry["md5"][f] = hashlib.md5(data).hexdigest()

@@ -107,7 +107,7 @@ struct Tile {
 };
 
 // ring sweeps: G lanes per segment, V double2 per lane, R rows in flight per group, T threads per block
-template <int G, int V, int R, int T>
+template <int G, int V, int R, int T, int MINB = 1>
 struct RingTile {
   static constexpr int GPB = T / G;
   static constexpr int CAP = 2 * G * V;
@@ -122,7 +122,7 @@ struct RingTile {
     using svi::Sweep;
 #define SVI_RING_PHI(S, C)                                                         \
   do {                                                                             \
-    auto kern = svi::k_sweep_ring<G, V, R, T, Sweep::Phi, S, C>;                   \
+    auto kern = svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, S, C>;                   \
     prep(kern);                                                                    \
     kern<<<blocks, T, kSmem, st>>>(P);                                             \
   } while (0)
@@ -133,12 +133,12 @@ struct RingTile {
 #undef SVI_RING_PHI
   }
   static void s3(const Params &P, cudaStream_t st, uint32_t blocks) {
-    auto kern = svi::k_sweep_ring<G, V, R, T, svi::Sweep::S3, false, false>;
+    auto kern = svi::k_sweep_ring<G, V, R, T, MINB, svi::Sweep::S3, false, false>;
     prep(kern);
     kern<<<blocks, T, kSmem, st>>>(P);
   }
   static int max_blocks_s3(int sms, uint32_t) {
-    auto kern = svi::k_sweep_ring<G, V, R, T, svi::Sweep::S3, false, false>;
+    auto kern = svi::k_sweep_ring<G, V, R, T, MINB, svi::Sweep::S3, false, false>;
     prep(kern);
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, kSmem) != cudaSuccess || per_sm < 1)
@@ -156,6 +156,18 @@ struct RingTile {
   }
 };
 
+#ifndef SVI_RING16_MINB
+#define SVI_RING16_MINB 1
+#endif
+#ifndef SVI_RING16_R
+#define SVI_RING16_R 4
+#endif
+#ifndef SVI_RING_T
+#define SVI_RING_T 128
+#endif
+#ifndef SVI_RING_MINB
+#define SVI_RING_MINB 3
+#endif
 void pick_ring(uint32_t k, Ops *o) {
   const char *off = getenv("SVI_LS_DISABLE_RING");
   if (off && off[0] == '1') return;
@@ -173,20 +185,20 @@ void pick_ring(uint32_t k, Ops *o) {
     }
   } else if (ld <= 208 && want_g != 16) {   // G = 8, V = ceil(ld/16) in 8..13
     switch ((ld + 15) / 16) {
-      case 8: RingTile<8, 8, 2, 128>::attach(o); break;
-      case 9: RingTile<8, 9, 2, 128>::attach(o); break;
-      case 10: RingTile<8, 10, 2, 128>::attach(o); break;
-      case 11: RingTile<8, 11, 2, 128>::attach(o); break;
-      case 12: RingTile<8, 12, 2, 128>::attach(o); break;
-      default: RingTile<8, 13, 2, 128>::attach(o); break;
+      case 8: RingTile<8, 8, 2, SVI_RING_T, SVI_RING_MINB>::attach(o); break;
+      case 9: RingTile<8, 9, 2, SVI_RING_T, SVI_RING_MINB>::attach(o); break;
+      case 10: RingTile<8, 10, 2, SVI_RING_T, SVI_RING_MINB>::attach(o); break;
+      case 11: RingTile<8, 11, 2, SVI_RING_T, SVI_RING_MINB>::attach(o); break;
+      case 12: RingTile<8, 12, 2, SVI_RING_T, SVI_RING_MINB>::attach(o); break;
+      default: RingTile<8, 13, 2, SVI_RING_T, SVI_RING_MINB>::attach(o); break;
     }
   } else {   // G = 16, V = ceil(ld/32) in 4..8
     switch ((ld + 31) / 32) {
-      case 4: RingTile<16, 4, 4, 256>::attach(o); break;
-      case 5: RingTile<16, 5, 4, 256>::attach(o); break;
-      case 6: RingTile<16, 6, 4, 256>::attach(o); break;
-      case 7: RingTile<16, 7, 4, 256>::attach(o); break;
-      default: RingTile<16, 8, 4, 256>::attach(o); break;
+      case 4: RingTile<16, 4, SVI_RING16_R, 256, SVI_RING16_MINB>::attach(o); break;
+      case 5: RingTile<16, 5, SVI_RING16_R, 256, SVI_RING16_MINB>::attach(o); break;
+      case 6: RingTile<16, 6, SVI_RING16_R, 256, SVI_RING16_MINB>::attach(o); break;
+      case 7: RingTile<16, 7, SVI_RING16_R, 256, SVI_RING16_MINB>::attach(o); break;
+      default: RingTile<16, 8, SVI_RING16_R, 256, SVI_RING16_MINB>::attach(o); break;
     }
   }
 }

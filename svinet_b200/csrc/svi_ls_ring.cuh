@@ -78,15 +78,119 @@ struct Ring {
 
 enum class Sweep { Phi, S3 };
 
+// fixed-shape pairwise tree over n values (latency log2(n) adds instead of n)
+template <int N>
+__device__ __forceinline__ double tree_sum(double (&t)[N]) {
+#pragma unroll
+  for (int n = N; n > 1; n = (n + 1) / 2) {
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) t[i] += t[n - 1 - i];
+  }
+  return t[0];
+}
+
+#ifndef SVI_PHI_VARIANT
+#define SVI_PHI_VARIANT 2   // 2 = two passes over the shared-memory row (default), 0 = weights kept in registers
+#endif
+#if SVI_PHI_VARIANT == 2
 // phi of one neighbour row sitting in shared memory at `rbase`, accumulated into acc (and the arg-max
 // community into mb).  `mask` is the shuffle mask: the full warp when every group of the warp is here,
 // the group's own lanes otherwise.
+//
+// Two passes over the shared-memory row instead of a register copy of the weights: pass 1 forms
+// s = sum_k be[k]*r[k] (and, for the tally, the arg-max of the products), pass 2 re-reads the row and
+// accumulates phi[k] = be[k] * (r[k] / s).  The row costs two LDS.128 per 16 bytes, but the 2V weight
+// registers are gone, which is what lets four blocks (16 warps) share an SM.
+template <int G, int V, bool SPARSE, bool COMM>
+__device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_t lane, unsigned mask,
+                                        const double2 (&be)[V], double2 (&acc)[V], uint32_t &mb, bool sparse,
+                                        uint32_t p, uint32_t q) {
+  // SPARSE: restrict to the union of the endpoints' active communities (:634-664); bit e of `keep`
+  // is element e = 2j + {0,1} of this lane
+  uint32_t keep = 0xffffffffu;
+  if (SPARSE && sparse) {
+    const uint32_t *ap = P.abits + (size_t)p * P.words, *aq = P.abits + (size_t)q * P.words;
+    keep = 0;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const uint32_t c = 2u * (lane + G * j);
+      uint32_t bits = 0;
+      if (c < P.k) bits = (ap[c >> 5] | aq[c >> 5]) >> (c & 31u);
+      keep |= (bits & 3u) << (2 * j);
+    }
+  }
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  // arg-max of the unnormalised weights (same arg-max as phi = w/s); the FIRST maximum wins
+  // (D1Array::max, src/matrix.hh:521-532).  Two independent chains (even / odd j) halve the exposed
+  // compare latency; the merge keeps the lower element on ties.
+  double best = 0.0, bestb = 0.0;
+  uint32_t beste = 0xffffffffu, besteb = 0xffffffffu;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    double2 r = lds2(rbase + 16u * (lane + G * j));
+    if (SPARSE) {
+      if (!((keep >> (2 * j)) & 1u)) r.x = 0.0;
+      if (!((keep >> (2 * j)) & 2u)) r.y = 0.0;
+    }
+    if (COMM) {
+      const double wx = be[j].x * r.x, wy = be[j].y * r.y;
+      const bool yy = wy > wx;
+      const double wm = yy ? wy : wx;
+      const uint32_t we = yy ? 2 * j + 1 : 2 * j;
+      if (j & 1) {
+        s2 += wx; s3 += wy;
+        if (wm > bestb) { bestb = wm; besteb = we; }
+      } else {
+        s0 += wx; s1 += wy;
+        if (wm > best) { best = wm; beste = we; }
+      }
+    } else if (j & 1) {
+      s2 = fma(be[j].x, r.x, s2);
+      s3 = fma(be[j].y, r.y, s3);
+    } else {
+      s0 = fma(be[j].x, r.x, s0);
+      s1 = fma(be[j].y, r.y, s1);
+    }
+  }
+  double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(mask, s, o);
+  // s == 0 only for an empty active union: phi stays all-zero (:634-664 with an empty list).  No early
+  // return: other groups of the warp may share the shuffles below.
+  const double inv = s > 0.0 ? 1.0 / s : 0.0;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    double2 r = lds2(rbase + 16u * (lane + G * j));
+    if (SPARSE) {
+      if (!((keep >> (2 * j)) & 1u)) r.x = 0.0;
+      if (!((keep >> (2 * j)) & 2u)) r.y = 0.0;
+    }
+    acc[j].x = fma(be[j].x, r.x * inv, acc[j].x);
+    acc[j].y = fma(be[j].y, r.y * inv, acc[j].y);
+  }
+  if (COMM) {
+    if (bestb > best || (bestb == best && besteb < beste)) { best = bestb; beste = besteb; }
+    uint32_t bestk = beste == 0xffffffffu ? beste : 2u * (lane + G * (beste >> 1)) + (beste & 1u);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(mask, best, o);
+      const uint32_t ok = __shfl_xor_sync(mask, bestk, o);
+      if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+    }
+    if (best > 0.0 && lane == (bestk >> 5)) mb |= 1u << (bestk & 31u);
+  }
+}
+
+#else
+// phi of one neighbour row sitting in shared memory at `rbase`, accumulated into acc (and the arg-max
+// community into mb).  `mask` is the shuffle mask: the full warp when every group of the warp is here,
+// the group's own lanes otherwise.  The lane-local sum and arg-max are evaluated as trees: with two
+// resident warps per scheduler a 2V-deep dependent chain of FP64 compares is pure exposed latency.
 template <int G, int V, bool SPARSE, bool COMM>
 __device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_t lane, unsigned mask,
                                         const double2 (&be)[V], double2 (&acc)[V], uint32_t &mb, bool sparse,
                                         uint32_t p, uint32_t q) {
   double2 w[V];
-  double s = 0.0;
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     const double2 r = lds2(rbase + 16u * (lane + G * j));
@@ -104,8 +208,10 @@ __device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_
       if (!(bits & 2u)) w[j].y = 0.0;
     }
   }
+  double t[V];
 #pragma unroll
-  for (int j = 0; j < V; ++j) s += w[j].x + w[j].y;
+  for (int j = 0; j < V; ++j) t[j] = w[j].x + w[j].y;
+  double s = tree_sum<V>(t);
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(mask, s, o);
   // s == 0 only for an empty active union: phi stays all-zero (:634-664 with an empty list).  No early
@@ -117,16 +223,28 @@ __device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_
     acc[j].y = fma(w[j].y, inv, acc[j].y);
   }
   if (COMM) {
-    // arg-max of the unnormalised weights (same arg-max as phi = w/s); first maximum wins
-    // (D1Array::max, src/matrix.hh:521-532)
-    double best = 0.0;
-    uint32_t bestk = 0xffffffffu;
+    // arg-max of the unnormalised weights (same arg-max as phi = w/s); the FIRST maximum wins
+    // (D1Array::max, src/matrix.hh:521-532): a tournament over neighbours in column order, where the
+    // later entry replaces the earlier one only when strictly larger, keeps exactly that rule
+    double bv[V];
+    uint32_t be_[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const uint32_t c = 2u * (lane + G * j);
-      if (w[j].x > best) { best = w[j].x; bestk = c; }
-      if (w[j].y > best) { best = w[j].y; bestk = c + 1u; }
+      const bool y = w[j].y > w[j].x;
+      bv[j] = y ? w[j].y : w[j].x;
+      be_[j] = y ? 2 * j + 1 : 2 * j;
     }
+#pragma unroll
+    for (int step = 1; step < V; step <<= 1) {
+#pragma unroll
+      for (int i = 0; i + step < V; i += 2 * step) {
+        const bool later = bv[i + step] > bv[i];
+        bv[i] = later ? bv[i + step] : bv[i];
+        be_[i] = later ? be_[i + step] : be_[i];
+      }
+    }
+    double best = bv[0];
+    uint32_t bestk = best > 0.0 ? 2u * (lane + G * (be_[0] >> 1)) + (be_[0] & 1u) : 0xffffffffu;
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
       const double ob = __shfl_xor_sync(mask, best, o);
@@ -137,11 +255,13 @@ __device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_
   }
 }
 
+#endif
+
 // One group per segment, 32/G segments per warp in lockstep.
 //   MODE == Phi : part[seg] = sum over the segment's neighbours of phi        (K1, src/linksampling.cc:605-725)
 //   MODE == S3  : block partials of s3[k] = sum mphi[p][k]*mphi[q][k]          (K3, :731-746)
-template <int G, int V, int R, int T, Sweep MODE, bool SPARSE, bool COMM>
-__global__ void __launch_bounds__(T) k_sweep_ring(const Params P) {
+template <int G, int V, int R, int T, int MINB, Sweep MODE, bool SPARSE, bool COMM>
+__global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P) {
   static_assert(R <= G && (R & (R - 1)) == 0, "ring depth: power of two, at most one chunk");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int GPB = T / G;        // groups per block
@@ -223,6 +343,9 @@ __global__ void __launch_bounds__(T) k_sweep_ring(const Params P) {
       q_nxt = nxt_live ? __ldg(P.col + beg + c0 + G + lane) : p;
       qc_nxt = 0;
       const uint32_t ulim = min((uint32_t)G, cntmax - c0);
+      // one copy of the body: unrolled G times with two phi_row instances each, the sweep is ~150 KB of
+      // SASS and runs out of the instruction cache
+#pragma unroll 1
       for (uint32_t u = 0; u < ulim; ++u) {
         const uint32_t i = c0 + u;
         if (u == 1 || ulim == 1) qc_nxt = nxt_live ? P.conv[q_nxt] : 0u;   // chunk c+1 flags, one row late
@@ -260,10 +383,8 @@ __global__ void __launch_bounds__(T) k_sweep_ring(const Params P) {
         } else {
           bool sparse = false;
           if (SPARSE) sparse = full && pa < P.k_div10 && P.active[q] < P.k_div10;
-          if (allfull) {
-            phi_row<G, V, SPARSE, COMM>(P, rbase, lane, 0xffffffffu, be, acc, mb, sparse, p, q);
-          } else if (full) {
-            phi_row<G, V, SPARSE, COMM>(P, rbase, lane, gmask, be, acc, mb, sparse, p, q);
+          if (full) {
+            phi_row<G, V, SPARSE, COMM>(P, rbase, lane, allfull ? 0xffffffffu : gmask, be, acc, mb, sparse, p, q);
           } else if (live) {
             const uint32_t c = (pc ? pc : qc) - 1u;   // one-hot phi, :622-631
 #pragma unroll

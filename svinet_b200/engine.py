@@ -50,7 +50,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or _build.LIB
+    path = path or os.environ.get("SVI_LS_LIB") or _build.LIB     # SVI_LS_LIB: development A/B override
     if not os.path.exists(path):
         raise SviError("%s not built: run `python -m svinet_b200.build` (needs nvcc)" % path)
     L = C.CDLL(path)

@@ -45,6 +45,15 @@ class OrcOptions(C.Structure):
                 ("reportfreq", C.c_uint32), ("eta0", C.c_double), ("eta1", C.c_double), ("epsilon", C.c_double)]
 
 
+class OrcFa2Options(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("seed", C.c_double), ("heldout_ratio", C.c_double),
+                ("max_iterations", C.c_uint32), ("reportfreq", C.c_uint32),
+                ("eta0", C.c_double), ("eta1", C.c_double), ("epsilon", C.c_double),
+                ("tau0", C.c_double), ("kappa", C.c_double), ("nodetau0", C.c_double), ("nodekappa", C.c_double),
+                ("online_iterations", C.c_uint32), ("meanchangethresh", C.c_double),
+                ("deterministic", C.c_int), ("nolambda", C.c_int)]
+
+
 def build():
     """(Re)build the C restatement; cheap (one gcc call)."""
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
@@ -54,8 +63,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(
-            os.path.join(ORACLE_DIR, "oracle_ls.c")):
+    if not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(
+            os.path.getmtime(os.path.join(ORACLE_DIR, f)) for f in ("oracle_ls.c", "oracle_fa2.c", "oracle_fa2.h")):
         build()
     L = C.CDLL(LIB_PATH)
     L.orc_graph_read.restype = C.POINTER(OrcGraph)
@@ -104,6 +113,40 @@ def lib():
     L.orc_rng_uniform.argtypes = [C.c_void_p]
     L.orc_rng_uniform_int.restype = C.c_ulong
     L.orc_rng_uniform_int.argtypes = [C.c_void_p, C.c_ulong]
+    # ---- oracle_fa2.h ----
+    vp = C.c_void_p
+    L.orc_fa2_options_default.argtypes = [C.POINTER(OrcFa2Options), C.c_uint32]
+    L.orc_fa2_create.restype = vp
+    L.orc_fa2_create.argtypes = [C.POINTER(OrcGraph), C.POINTER(OrcFa2Options)]
+    L.orc_fa2_free.argtypes = [vp]
+    L.orc_fa2_phi_pair.restype = C.c_uint32
+    L.orc_fa2_phi_pair.argtypes = [C.c_uint32, vp, vp, vp, C.c_int, C.c_double, C.c_uint32, C.c_double, vp, vp]
+    L.orc_fa2_plan.argtypes = [vp]
+    L.orc_fa2_process.argtypes = [vp]
+    L.orc_fa2_run.restype = C.c_uint32
+    L.orc_fa2_run.argtypes = [vp, C.c_uint32]
+    for fn in ("orc_fa2_n", "orc_fa2_k", "orc_fa2_iter", "orc_fa2_plan_type", "orc_fa2_plan_start"):
+        getattr(L, fn).restype = C.c_uint32
+        getattr(L, fn).argtypes = [vp]
+    for fn in ("orc_fa2_plan_npairs", "orc_fa2_total_pairs_sampled", "orc_fa2_nheldout"):
+        getattr(L, fn).restype = C.c_uint64
+        getattr(L, fn).argtypes = [vp]
+    L.orc_fa2_stopped.restype = C.c_int
+    L.orc_fa2_stopped.argtypes = [vp]
+    for fn in ("orc_fa2_gamma", "orc_fa2_lambda"):
+        getattr(L, fn).restype = C.POINTER(C.c_double)
+        getattr(L, fn).argtypes = [vp]
+    L.orc_fa2_alpha.restype = C.c_double
+    L.orc_fa2_alpha.argtypes = [vp]
+    for fn in ("orc_fa2_shuffled", "orc_fa2_plan_pairs", "orc_fa2_heldout_pairs", "orc_fa2_heldout_sorted"):
+        getattr(L, fn).restype = C.POINTER(C.c_uint32)
+        getattr(L, fn).argtypes = [vp]
+    L.orc_fa2_edge_likelihood.restype = C.c_double
+    L.orc_fa2_edge_likelihood.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int]
+    L.orc_fa2_heldout_log.restype = C.c_char_p
+    L.orc_fa2_heldout_log.argtypes = [vp]
+    L.orc_fa2_write_outputs.restype = C.c_int
+    L.orc_fa2_write_outputs.argtypes = [vp, C.c_char_p]
     _lib = L
     return L
 
@@ -254,3 +297,76 @@ class Rng:
 
     def uniform_int(self, n):
         return lib().orc_rng_uniform_int(self.buf, n)
+
+
+class Fa2Model:
+    """ctor + infer() of the reference's FastAMM2 (`-rnode -stratified`), restated (oracle/oracle_fa2.c)."""
+
+    def __init__(self, graph, k, **opts):
+        L = lib()
+        o = OrcFa2Options()
+        L.orc_fa2_options_default(C.byref(o), k)
+        for key, v in opts.items():
+            if not hasattr(o, key):
+                raise KeyError(key)
+            setattr(o, key, v)
+        self.graph, self.opts = graph, o
+        self.ptr = L.orc_fa2_create(graph.ptr, C.byref(o))
+        self.n, self.k = L.orc_fa2_n(self.ptr), L.orc_fa2_k(self.ptr)
+
+    gamma = property(lambda self: _view(lib().orc_fa2_gamma(self.ptr), (self.n, self.k), np.float64))
+    lambda_ = property(lambda self: _view(lib().orc_fa2_lambda(self.ptr), (self.k, 2), np.float64))
+    iter = property(lambda self: lib().orc_fa2_iter(self.ptr))
+    stopped = property(lambda self: bool(lib().orc_fa2_stopped(self.ptr)))
+    alpha = property(lambda self: lib().orc_fa2_alpha(self.ptr))
+    shuffled = property(lambda self: _view(lib().orc_fa2_shuffled(self.ptr), (self.n,), np.uint32))
+    total_pairs_sampled = property(lambda self: lib().orc_fa2_total_pairs_sampled(self.ptr))
+
+    def plan(self):
+        """RNG draws + pair selection of the next iteration: (type, start, pairs[np,2])."""
+        L = lib()
+        L.orc_fa2_plan(self.ptr)
+        npairs = L.orc_fa2_plan_npairs(self.ptr)
+        pairs = _view(L.orc_fa2_plan_pairs(self.ptr), (npairs, 2), np.uint32).copy()
+        return L.orc_fa2_plan_type(self.ptr), L.orc_fa2_plan_start(self.ptr), pairs
+
+    def process(self):
+        lib().orc_fa2_process(self.ptr)
+
+    def run(self, max_steps=0):
+        return lib().orc_fa2_run(self.ptr, max_steps)
+
+    def heldout_pairs(self, sorted_=True):
+        L = lib()
+        n = L.orc_fa2_nheldout(self.ptr)
+        fn = L.orc_fa2_heldout_sorted if sorted_ else L.orc_fa2_heldout_pairs
+        return _view(fn(self.ptr), (n, 2), np.uint32).copy()
+
+    def edge_likelihood(self, p, q, y):
+        return lib().orc_fa2_edge_likelihood(self.ptr, p, q, y)
+
+    def heldout_log(self):
+        return lib().orc_fa2_heldout_log(self.ptr).decode()
+
+    def write_outputs(self, d):
+        os.makedirs(d, exist_ok=True)
+        if lib().orc_fa2_write_outputs(self.ptr, d.encode()) != 0:
+            raise IOError("oracle: cannot write outputs to %s" % d)
+
+    def close(self):
+        if self.ptr:
+            lib().orc_fa2_free(self.ptr)
+            self.ptr = None
+
+
+def fa2_phi_pair(elogpi_p, elogpi_q, elogf, y, logepsilon=None, online_iterations=50, thresh=1e-5):
+    """PhiCompute::update_phis_until_conv for one pair: returns (phi1, phi2, rounds)."""
+    k = len(elogf)
+    a = np.ascontiguousarray(elogpi_p, dtype=np.float64)
+    b = np.ascontiguousarray(elogpi_q, dtype=np.float64)
+    f = np.ascontiguousarray(elogf, dtype=np.float64)
+    p1, p2 = np.empty(k), np.empty(k)
+    le = float(np.log(1e-30)) if logepsilon is None else logepsilon
+    r = lib().orc_fa2_phi_pair(k, a.ctypes.data, b.ctypes.data, f.ctypes.data, int(y), le, online_iterations, thresh,
+                               p1.ctypes.data, p2.ctypes.data)
+    return p1, p2, r

@@ -33,8 +33,9 @@ def _flags_to_opts(flags):
     return o
 
 
-FAST = [c for c in MANIFEST if not c.startswith("c2_")]
-SLOW = [c for c in MANIFEST if c.startswith("c2_")]
+LS = [c for c in MANIFEST if MANIFEST[c].get("mode", "-link-sampling") == "-link-sampling"]
+FAST = [c for c in LS if not c.startswith("c2_")]
+SLOW = [c for c in LS if c.startswith("c2_")]
 
 
 def _run_case(case):
