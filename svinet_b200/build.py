@@ -32,8 +32,8 @@ def _newer(target, sources):
 
 
 def build_lib(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, "svi_ls.cu")]
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [os.path.join(REPO, "include", "svi_ls.h")]
+    srcs = [os.path.join(CSRC, "svi_ls.cu"), os.path.join(CSRC, "svi_fa2.cu")]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [os.path.join(CSRC, "svi_common.h"), os.path.join(REPO, "include", "svi_ls.h"), os.path.join(REPO, "include", "svi_fa2.h")]
     os.makedirs(LIBDIR, exist_ok=True)
     if not force and not _newer(LIB, deps):
         return LIB

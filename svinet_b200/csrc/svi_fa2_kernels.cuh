@@ -1,0 +1,504 @@
+// svi_fa2_kernels.cuh -- sm_100a kernels of the `-rnode -stratified` iteration (class FastAMM2).
+//
+// What one iteration is (src/fastamm2.cc:566-640): a minibatch of node pairs that all contain one
+// start node (its links, or a "non-informative" set of n/10 non-links); every pair runs a two-phi
+// coordinate ascent (PhiCompute::update_phis_until_conv, src/fastamm2.hh:151-209, <= 50 rounds of two
+// K-wide softmaxes); phi of the far endpoint becomes that node's gammat row, phi of the start node and
+// phi1*phi2 are summed over the minibatch; then EVERY gamma row is blended (touched rows towards
+// alpha + scale*gammat, all other rows decay towards alpha) and lambda is blended.
+//
+// Device formulation:
+//   k_fa2_prep   one block: Elogbeta = psi(lambda) - psi(sum), Elogf = column `type` of it, Elogpi of
+//                the start node (the far endpoints' Elogpi rows are formed by the pair kernel from
+//                their gamma rows: no N x K Elogpi matrix exists)
+//   k_fa2_pairs  persistent; a GROUP of G lanes owns one pair, the whole fixed point runs in registers;
+//                the far endpoint is touched by exactly one pair, so its Robbins-Monro blend is done
+//                right there; start-node phi and phi1*phi2 go to per-group shared-memory accumulators
+//                and leave as per-block partial rows (fixed order: run-to-run deterministic)
+//   k_fa2_blend  every other row: decay towards alpha (the bandwidth-bound pass, 2 x N x K x 8 bytes);
+//                the start row gets the reduced partials
+//   k_fa2_lambda one block: reduce the phi1*phi2 partials, blend lambda, advance the node counter
+//   k_fa2_draw   one block: the minibatch itself, from a Philox4x32-10 stream keyed by (seed, iter)
+#pragma once
+#include "svi_ls_kernels.cuh"
+
+namespace svi {
+
+struct Fa2Ctrl {            // one iteration's control block, device resident
+  uint32_t type, start, npairs, iter;
+  uint64_t sampled_inc;     // the reference's _total_pairs_sampled increment
+  double rho_node, rho_t, scale;
+  double nodec;             // _nodec[i] (identical for every node: each is bumped every iteration)
+  uint64_t total_sampled, total_rounds, last_rounds;
+};
+
+struct Fa2Params {
+  uint32_t n, k, ld;
+  double alpha, eta0, eta1, logeps, thresh, epsilon;
+  double tau0, kappa, nodetau0, nodekappa, inf_epsilon;
+  uint32_t online_iters, m_sets, nolambda;
+  double *gamma;            // [n*ld]
+  double *lambda;           // [k*2]
+  double *elogbeta;         // [2*ld]  column 0 then column 1
+  double *elogf;            // [ld]    -inf beyond k
+  double *epi_start;        // [ld]    -inf beyond k
+  uint32_t *pairs;          // [2*cap_pairs]
+  uint32_t cap_pairs;
+  uint8_t *touched;         // [n]
+  Fa2Ctrl *ctrl;
+  double *partS, *partL;    // [pair_blocks * cap] block partials
+  uint32_t pair_blocks;
+  // graph for device-side draws
+  const uint64_t *adj_off;  // [n+1]
+  const uint32_t *adj;      // sorted neighbour lists
+  const uint64_t *heldout;  // sorted (p<<32|q)
+  uint64_t nheldout;
+  const uint32_t *shuffled; // [n]
+};
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter = (c0,c1,c2,c3), key = (k0,k1) -------------------
+__host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+// ---- K-wide softmax of t[] over the group, in place: t <- exp(t - logsumexp(t)) -------------------
+// (D1Array::lognormalize, src/matrix.hh:296-318, evaluated as max / sum-of-exp instead of the running
+// pairwise log-sum; pad columns hold -inf and come out as 0)
+template <int G, int V>
+__device__ __forceinline__ void group_softmax(double2 (&t)[V], unsigned mask) {
+  double m = -CUDART_INF;
+#pragma unroll
+  for (int j = 0; j < V; ++j) m = fmax(m, fmax(t[j].x, t[j].y));
+  m = group_max<G>(m, mask);
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    t[j].x = exp(t[j].x - m);
+    t[j].y = exp(t[j].y - m);
+    s += t[j].x + t[j].y;
+  }
+  s = group_sum<G>(s, mask);
+  const double inv = 1.0 / s;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    t[j].x *= inv;
+    t[j].y *= inv;
+  }
+}
+
+// Elogpi row of node a from its gamma row (FastAMM2::set_dir_exp(a,..), src/fastamm2.hh:424-435);
+// pad columns -> -inf
+template <int G, int V>
+__device__ __forceinline__ void elogpi_row(const Fa2Params &P, uint32_t a, uint32_t lane, unsigned mask,
+                                           double2 (&e)[V]) {
+  const double *row = P.gamma + (size_t)a * P.ld;
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    e[j] = ld_row2(row, 2u * (lane + G * j), P.ld);
+    s += e[j].x + e[j].y;                       // pad columns hold 0
+  }
+  s = group_sum<G>(s, mask);
+  const double psi_sum = digamma_pos(s);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const uint32_t c = 2u * (lane + G * j);
+    e[j].x = c < P.k ? digamma_pos(e[j].x) - psi_sum : -CUDART_INF;
+    e[j].y = c + 1u < P.k ? digamma_pos(e[j].y) - psi_sum : -CUDART_INF;
+  }
+}
+
+// The coordinate ascent of one pair.  ep/eq: Elogpi rows of p and q; ef: Elogf; on return phi1/phi2.
+// Returns the number of rounds.  Both sides of a round read the OLD phis (update_phis does not write
+// _phi1/_phi2 when phifix is false, src/fastamm2.hh:129-135); convergence is tested on odd rounds against
+// the phis of two rounds earlier (:170-199).
+template <int G, int V>
+__device__ __forceinline__ uint32_t fa2_pair_core(const Fa2Params &P, unsigned mask, int y,
+                                                  const double2 (&ep)[V], const double2 (&eq)[V],
+                                                  const double2 (&ef)[V], uint32_t lane,
+                                                  double2 (&phi1)[V], double2 (&phi2)[V]) {
+  const double u0 = 1.0 / (double)P.k;
+  double2 old1[V], old2[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const uint32_t c = 2u * (lane + G * j);
+    phi1[j] = make_double2(c < P.k ? u0 : 0.0, c + 1u < P.k ? u0 : 0.0);
+    phi2[j] = phi1[j];
+    old1[j] = old2[j] = make_double2(0.0, 0.0);
+  }
+  const double inv_k = 1.0 / (double)P.k;   // mean() divides by k; x/k vs x*(1/k) only matters at the threshold's last ulp
+  uint32_t rounds = 0;
+  for (uint32_t i = 0; i < P.online_iters; ++i) {
+    if ((i & 1u) == 0u) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) { old1[j] = phi1[j]; old2[j] = phi2[j]; }
+    }
+    double2 t1[V], t2[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      // anext[k] = Elogpi[c][k] + Elogf[k]*b[k] + [y=1](1-b[k])*log(eps)      (src/fastamm2.hh:112-118)
+      double ux = 0.0, uy = 0.0, wx = 0.0, wy = 0.0;
+      if (y) {
+        ux = (1.0 - phi2[j].x) * P.logeps; uy = (1.0 - phi2[j].y) * P.logeps;
+        wx = (1.0 - phi1[j].x) * P.logeps; wy = (1.0 - phi1[j].y) * P.logeps;
+      }
+      t1[j].x = ep[j].x + ef[j].x * phi2[j].x + ux;
+      t1[j].y = ep[j].y + ef[j].y * phi2[j].y + uy;
+      t2[j].x = eq[j].x + ef[j].x * phi1[j].x + wx;
+      t2[j].y = eq[j].y + ef[j].y * phi1[j].y + wy;
+    }
+    group_softmax<G, V>(t1, mask);
+    group_softmax<G, V>(t2, mask);
+    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      d1 += fabs(t1[j].x - old1[j].x) + fabs(t1[j].y - old1[j].y);
+      d2 += fabs(t2[j].x - old2[j].x) + fabs(t2[j].y - old2[j].y);
+      phi1[j] = t1[j];
+      phi2[j] = t2[j];
+    }
+    rounds++;
+    if ((i & 1u) == 0u) continue;
+    d1 = group_sum<G>(d1, mask);
+    d2 = group_sum<G>(d2, mask);
+    if (d1 * inv_k < P.thresh && d2 * inv_k < P.thresh) break;
+  }
+  return rounds;
+}
+
+template <int G, int V>
+__device__ __forceinline__ void load_kvec(const double *v, uint32_t lane, uint32_t ld, double2 (&o)[V], double pad) {
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const uint32_t c = 2u * (lane + G * j);
+    o[j] = c < ld ? *reinterpret_cast<const double2 *>(v + c) : make_double2(pad, pad);
+  }
+}
+
+// ---- prep: expectations shared by the whole minibatch ---------------------------------------------
+template <int G, int V>
+__global__ void __launch_bounds__(128) k_fa2_prep(const Fa2Params P) {
+  const Fa2Ctrl c = *P.ctrl;
+  if (threadIdx.x == 0) P.ctrl->last_rounds = 0;
+  for (uint32_t z = threadIdx.x; z < P.ld; z += blockDim.x) {
+    double e0 = -CUDART_INF, e1 = -CUDART_INF;
+    if (z < P.k) {
+      // FastAMM2::set_dir_exp(lambda, Elogbeta), src/fastamm2.hh:401-422 (non-positive -> alpha)
+      const double l0 = P.lambda[2 * z], l1 = P.lambda[2 * z + 1];
+      const double ps = digamma_pos(l0 + l1);
+      e0 = digamma_pos(l0 <= 0.0 ? P.alpha : l0) - ps;
+      e1 = digamma_pos(l1 <= 0.0 ? P.alpha : l1) - ps;
+    }
+    P.elogbeta[z] = e0;
+    P.elogbeta[P.ld + z] = e1;
+    // compute_Elogf (src/fastamm2.hh:139-149): y = 1 -> column 0, y = 0 -> column 1
+    P.elogf[z] = z < P.k ? (c.type == 0 ? e0 : e1) : 0.0;
+  }
+  if (threadIdx.x < G) {   // Elogpi of the start node, by the first group
+    const unsigned mask = group_mask<G>();
+    double2 e[V];
+    elogpi_row<G, V>(P, c.start, threadIdx.x, mask, e);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const uint32_t col = 2u * (threadIdx.x + G * j);
+      if (col < P.ld) *reinterpret_cast<double2 *>(P.epi_start + col) = e[j];
+    }
+  }
+}
+
+// ---- the pairs -------------------------------------------------------------------------------------
+template <int G, int V, int T>
+__global__ void __launch_bounds__(T) k_fa2_pairs(const Fa2Params P) {
+  extern __shared__ double smem[];
+  constexpr int CAP = 2 * G * V;
+  constexpr int GPB = T / G;
+  double *accS = smem;                 // [GPB][CAP] start-node phi, summed over this group's pairs
+  double *accL = smem + GPB * CAP;     // [GPB][CAP] phi1*phi2
+  const unsigned mask = group_mask<G>();
+  const uint32_t lane = threadIdx.x & (G - 1), grp = threadIdx.x / G;
+  const Fa2Ctrl c = *P.ctrl;
+  const int y = c.type == 0 ? 1 : 0;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(2 * GPB * CAP); i += T) smem[i] = 0.0;
+  __syncthreads();
+  double *myS = accS + grp * CAP, *myL = accL + grp * CAP;
+
+  double2 ef[V], es[V];
+  load_kvec<G, V>(P.elogf, lane, P.ld, ef, 0.0);
+  load_kvec<G, V>(P.epi_start, lane, P.ld, es, -CUDART_INF);
+  uint32_t my_rounds = 0;
+  const uint32_t ngroups = gridDim.x * GPB;
+  for (uint32_t i = blockIdx.x * GPB + grp; i < c.npairs; i += ngroups) {
+    const uint32_t p = P.pairs[2 * i], q = P.pairs[2 * i + 1];
+    const bool start_is_p = p == c.start;
+    const uint32_t a = start_is_p ? q : p;
+    double2 ea[V], phi1[V], phi2[V];
+    elogpi_row<G, V>(P, a, lane, mask, ea);
+    uint32_t r;
+    if (start_is_p) r = fa2_pair_core<G, V>(P, mask, y, es, ea, ef, lane, phi1, phi2);
+    else r = fa2_pair_core<G, V>(P, mask, y, ea, es, ef, lane, phi1, phi2);
+    if (lane == 0) my_rounds += r;
+    // far endpoint: gammat[a] = its phi, touched exactly once -> blend here (src/fastamm2.cc:609-613)
+    double *grow = P.gamma + (size_t)a * P.ld;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const uint32_t col = 2u * (lane + G * j);
+      const double2 pa = start_is_p ? phi2[j] : phi1[j];
+      const double2 ps = start_is_p ? phi1[j] : phi2[j];
+      if (col < P.ld) {
+        double2 g = *reinterpret_cast<const double2 *>(grow + col);
+        g.x = col < P.k ? (1.0 - c.rho_node) * g.x + c.rho_node * (P.alpha + c.scale * pa.x) : 0.0;
+        g.y = col + 1u < P.k ? (1.0 - c.rho_node) * g.y + c.rho_node * (P.alpha + c.scale * pa.y) : 0.0;
+        *reinterpret_cast<double2 *>(grow + col) = g;
+      }
+      myS[col] += ps.x;
+      myS[col + 1] += ps.y;
+      myL[col] += phi1[j].x * phi2[j].x;       // lambdat[k][t] += phi1*phi2 (src/fastamm2.cc:994-996)
+      myL[col + 1] += phi1[j].y * phi2[j].y;
+    }
+    if (lane == 0) P.touched[a] = 1;
+  }
+  __syncthreads();
+  for (uint32_t col = threadIdx.x; col < (uint32_t)CAP; col += T) {
+    double s = 0.0, l = 0.0;
+    for (int g = 0; g < GPB; ++g) { s += accS[g * CAP + col]; l += accL[g * CAP + col]; }
+    P.partS[(size_t)blockIdx.x * CAP + col] = s;
+    P.partL[(size_t)blockIdx.x * CAP + col] = l;
+  }
+  if (lane == 0 && my_rounds) atomicAdd((unsigned long long *)&P.ctrl->last_rounds, (unsigned long long)my_rounds);
+}
+
+// ---- blend of all the rows the pair kernel did not touch (src/fastamm2.cc:605-624) -----------------
+template <int G, int V, int T>
+__global__ void __launch_bounds__(T) k_fa2_blend(const Fa2Params P) {
+  constexpr int CAP = 2 * G * V;
+  const uint32_t lane = threadIdx.x & (G - 1);
+  const uint32_t i = (blockIdx.x * T + threadIdx.x) / G;
+  if (i >= P.n) return;
+  const Fa2Ctrl c = *P.ctrl;
+  if (P.touched[i]) {
+    if (lane == 0) P.touched[i] = 0;
+    return;
+  }
+  double *grow = P.gamma + (size_t)i * P.ld;
+  const bool is_start = i == c.start;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const uint32_t col = 2u * (lane + G * j);
+    if (col >= P.ld) continue;
+    double2 t = make_double2(0.0, 0.0);
+    if (is_start) {
+      for (uint32_t b = 0; b < P.pair_blocks; ++b) {
+        const double2 v = *reinterpret_cast<const double2 *>(P.partS + (size_t)b * CAP + col);
+        t.x += v.x;
+        t.y += v.y;
+      }
+    }
+    double2 g = *reinterpret_cast<const double2 *>(grow + col);
+    const double tx = is_start ? P.alpha + c.scale * t.x : P.alpha;
+    const double ty = is_start ? P.alpha + c.scale * t.y : P.alpha;
+    g.x = col < P.k ? (1.0 - c.rho_node) * g.x + c.rho_node * tx : 0.0;
+    g.y = col + 1u < P.k ? (1.0 - c.rho_node) * g.y + c.rho_node * ty : 0.0;
+    *reinterpret_cast<double2 *>(grow + col) = g;
+  }
+}
+
+// ---- lambda blend (src/fastamm2.cc:626-638) + counters ----------------------------------------------
+static __global__ void k_fa2_lambda(const Fa2Params P, uint32_t cap) {
+  const Fa2Ctrl c = *P.ctrl;
+  if (!P.nolambda) {
+    for (uint32_t z = threadIdx.x; z < P.k; z += blockDim.x) {
+      double s = 0.0;
+      for (uint32_t b = 0; b < P.pair_blocks; ++b) s += P.partL[(size_t)b * cap + z];
+      for (uint32_t t = 0; t < 2; ++t) {
+        const double raw = t == c.type ? s : 0.0;            // phi1*phi2*(t==0 ? y : 1-y)
+        const double ldt = (t == 0 ? P.eta0 : P.eta1) + c.scale * raw;
+        P.lambda[2 * z + t] = (1.0 - c.rho_t) * P.lambda[2 * z + t] + c.rho_t * ldt;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Fa2Ctrl *w = P.ctrl;
+    w->nodec = c.nodec + 1.0;
+    w->total_sampled = c.total_sampled + c.sampled_inc;
+    w->total_rounds = c.total_rounds + c.last_rounds;
+  }
+}
+
+// ---- device-side minibatch draw -----------------------------------------------------------------------
+__device__ __forceinline__ bool fa2_is_link(const Fa2Params &P, uint32_t a, uint32_t b) {
+  uint64_t lo = P.adj_off[a], hi = P.adj_off[a + 1];
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    const uint32_t v = P.adj[mid];
+    if (v == b) return true;
+    if (v < b) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+__device__ __forceinline__ bool fa2_is_heldout(const Fa2Params &P, uint32_t a, uint32_t b) {
+  const uint64_t key = ((uint64_t)min(a, b) << 32) | max(a, b);
+  uint64_t lo = 0, hi = P.nheldout;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    const uint64_t v = P.heldout[mid];
+    if (v == key) return true;
+    if (v < key) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+// One block.  Order-preserving compaction of the candidates (block scan per chunk of blockDim.x):
+//   type 0: the start node's neighbours minus held-out pairs                  (src/fastamm2.cc:943-960)
+//   type 1: walk the shuffled node order from a random block boundary, keep non-links that are not held
+//           out, until n/m nodes are collected                                (src/fastamm2.cc:1095-1125)
+static __global__ void __launch_bounds__(1024) k_fa2_draw(const Fa2Params P, uint32_t iter, uint32_t seed_lo, uint32_t seed_hi) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t s_base, s_done;
+  uint32_t r[4] = {iter, 0u, 0u, 0u};
+  philox4x32_10(r, seed_lo, seed_hi);
+  const uint32_t type = (double)r[0] * (1.0 / 4294967296.0) < P.inf_epsilon ? 1u : 0u;   // gsl_ran_bernoulli
+  const uint32_t start = __umulhi(r[1], P.n);
+  const uint32_t setsize = (uint32_t)((double)P.n / (double)P.m_sets);
+  const uint32_t lanei = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_base = 0; s_done = 0; }
+  __syncthreads();
+  uint64_t ncand;
+  uint32_t q0 = 0, want;
+  if (type == 0) {
+    ncand = P.adj_off[start + 1] - P.adj_off[start];
+    want = 0xffffffffu;
+  } else {
+    q0 = setsize ? (__umulhi(r[2], P.n) / setsize) * setsize : 0u;
+    ncand = P.n;          // at most one lap over the shuffled order
+    want = setsize;
+  }
+  for (uint64_t c0 = 0; c0 < ncand; c0 += blockDim.x) {
+    const uint64_t ci = c0 + threadIdx.x;
+    uint32_t node = 0;
+    bool ok = false;
+    if (ci < ncand) {
+      if (type == 0) {
+        node = P.adj[P.adj_off[start] + ci];
+        ok = !fa2_is_heldout(P, start, node);
+      } else {
+        node = P.shuffled[(q0 + ci) % P.n];
+        ok = node != start && !fa2_is_link(P, start, node) && !fa2_is_heldout(P, start, node);
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+    const uint32_t before = __popc(bal & ((1u << lanei) - 1u));
+    if (lanei == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t off = s_base;
+    for (uint32_t w = 0; w < warp; ++w) off += warp_tot[w];
+    const uint32_t pos = off + before;
+    if (ok && pos < want && pos < P.cap_pairs) {
+      P.pairs[2 * pos] = min(start, node);
+      P.pairs[2 * pos + 1] = max(start, node);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tot = 0;
+      for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) tot += warp_tot[w];
+      s_base += tot;
+      if (s_base >= want) s_done = 1;
+    }
+    __syncthreads();
+    if (s_done) break;
+  }
+  if (threadIdx.x == 0) {
+    Fa2Ctrl *w = P.ctrl;
+    const uint32_t np = min(min(s_base, want), P.cap_pairs);
+    w->type = type;
+    w->start = start;
+    w->npairs = np;
+    w->iter = iter;
+    w->sampled_inc = type == 0 ? ncand : np;
+    w->last_rounds = 0;
+    w->rho_node = pow(P.nodetau0 + w->nodec, -1.0 * P.nodekappa);              // :606
+    w->rho_t = pow(P.tau0 + ((double)iter + 1.0), -1.0 * P.kappa);             // :627, _lambda_start_iter = 0
+    w->scale = type == 0 ? (double)P.n / (2.0 * (1.0 - P.inf_epsilon))         // :591-592
+                         : ((double)P.n * (double)P.m_sets) / (2.0 * P.inf_epsilon);
+  }
+}
+
+// ---- FastAMM2::edge_likelihood (src/fastamm2.hh:477-520) ---------------------------------------------
+template <int G, int V>
+__global__ void __launch_bounds__(128) k_fa2_heldout(const Fa2Params P, uint64_t npairs, const uint32_t *pp,
+                                                     const uint32_t *qq, const uint8_t *yy, double *out) {
+  const unsigned mask = group_mask<G>();
+  const uint32_t lane = threadIdx.x & (G - 1);
+  const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (i >= npairs) return;
+  const uint32_t p = pp[i], q = qq[i];
+  const int y = yy[i];
+  double2 gp[V], gq[V];
+  double sp = 0.0, sq = 0.0;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const uint32_t c0 = 2u * (lane + G * j);
+    gp[j] = ld_row2(P.gamma + (size_t)p * P.ld, c0, P.ld);
+    gq[j] = ld_row2(P.gamma + (size_t)q * P.ld, c0, P.ld);
+    sp += gp[j].x + gp[j].y;
+    sq += gq[j].x + gq[j].y;
+  }
+  sp = group_sum<G>(sp, mask);
+  sq = group_sum<G>(sq, mask);
+  double s = 0.0, sum = 0.0;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const uint32_t c0 = 2u * (lane + G * j);
+    double2 rate = make_double2(0.0, 0.0);
+    if (c0 < P.k) rate.x = P.lambda[2 * c0] / (P.lambda[2 * c0] + P.lambda[2 * c0 + 1]);
+    if (c0 + 1u < P.k) rate.y = P.lambda[2 * c0 + 2] / (P.lambda[2 * c0 + 2] + P.lambda[2 * c0 + 3]);
+    const double ax = (gp[j].x / sp) * (gq[j].x / sq), ay = (gp[j].y / sp) * (gq[j].y / sq);
+    if (y) {
+      s += ax * rate.x + ay * rate.y;
+    } else {
+      s += ax * (1.0 - rate.x) + ay * (1.0 - rate.y);
+      sum += ax + ay;
+    }
+  }
+  s = group_sum<G>(s, mask);
+  if (!y) {
+    sum = group_sum<G>(sum, mask);
+    s += (1.0 - sum) * (1.0 - P.epsilon);
+  }
+  if (s < 1e-30) s = 1e-30;
+  if (lane == 0) out[i] = log(s);
+}
+
+// ---- one pair, no side effects (svi_fa2_phi_pair) ------------------------------------------------------
+template <int G, int V>
+__global__ void __launch_bounds__(32) k_fa2_one_pair(const Fa2Params P, uint32_t p, uint32_t q, int y, double *phi_out,
+                                                     uint32_t *rounds_out) {
+  if (threadIdx.x >= G) return;
+  const unsigned mask = group_mask<G>();
+  const uint32_t lane = threadIdx.x;
+  double2 ep[V], eq[V], ef[V], phi1[V], phi2[V];
+  elogpi_row<G, V>(P, p, lane, mask, ep);
+  elogpi_row<G, V>(P, q, lane, mask, eq);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const uint32_t c = 2u * (lane + G * j);
+    ef[j].x = c < P.k ? P.elogbeta[(y ? 0 : P.ld) + c] : 0.0;
+    ef[j].y = c + 1u < P.k ? P.elogbeta[(y ? 0 : P.ld) + c + 1] : 0.0;
+  }
+  const uint32_t r = fa2_pair_core<G, V>(P, mask, y, ep, eq, ef, lane, phi1, phi2);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const uint32_t c = 2u * (lane + G * j);
+    if (c < P.k) { phi_out[c] = phi1[j].x; phi_out[P.k + c] = phi2[j].x; }
+    if (c + 1u < P.k) { phi_out[c + 1] = phi1[j].y; phi_out[P.k + c + 1] = phi2[j].y; }
+  }
+  if (lane == 0) *rounds_out = r;
+}
+
+}  // namespace svi

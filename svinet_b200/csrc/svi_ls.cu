@@ -4,6 +4,7 @@
 // dispatch by K, stream plumbing.  No CPU compute fallback exists: every entry point that
 // needs the GPU fails with SVI_ERR_CUDA when there is none.
 #include "../../include/svi_ls.h"
+#include "svi_common.h"
 #include "svi_ls_kernels.cuh"
 #include "svi_ls_ring.cuh"
 
@@ -15,10 +16,10 @@
 #include <new>
 #include <vector>
 
-namespace {
-
+namespace svi {
 thread_local char g_err[512] = "";
 
+// shared with svi_fa2.cu (svi_common.h)
 int fail(int code, const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -26,6 +27,11 @@ int fail(int code, const char *fmt, ...) {
   va_end(ap);
   return code;
 }
+}  // namespace svi
+
+namespace {
+using svi::fail;
+using svi::g_err;
 
 #define CK(call)                                                                          \
   do {                                                                                    \

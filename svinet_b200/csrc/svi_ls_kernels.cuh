@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256) k_node(const Params P) {
 }
 
 // fixed-order final reduction of `nvec` column vectors over `nblocks` block partials
-__global__ void k_reduce_kpart(const double *kpart, uint32_t nblocks, uint32_t nvec, uint32_t cap,
+static __global__ void k_reduce_kpart(const double *kpart, uint32_t nblocks, uint32_t nvec, uint32_t cap,
                                double *kvec, uint32_t ld) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec * ld; i += gridDim.x * blockDim.x) {
     const uint32_t v = i / ld, c = i % ld;
@@ -599,19 +599,19 @@ __global__ void __launch_bounds__(256) k_heldout(const Params P, uint64_t npairs
   if (lane == 0) out[i] = log(s);
 }
 
-__global__ void k_fill(double *p, size_t n, double v) {
+static __global__ void k_fill(double *p, size_t n, double v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
 // repack between the caller's dense [n*k] layout and the padded [n*ld] device layout
-__global__ void k_pad_rows(const double *src, double *dst, uint32_t n, uint32_t k, uint32_t ld) {
+static __global__ void k_pad_rows(const double *src, double *dst, uint32_t n, uint32_t k, uint32_t ld) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n * ld;
        i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t c = i % ld;
     dst[i] = c < k ? src[(i / ld) * k + c] : 0.0;
   }
 }
-__global__ void k_unpad_rows(const double *src, double *dst, uint32_t n, uint32_t k, uint32_t ld) {
+static __global__ void k_unpad_rows(const double *src, double *dst, uint32_t n, uint32_t k, uint32_t ld) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n * k;
        i += (size_t)gridDim.x * blockDim.x)
     dst[i] = src[(i / k) * ld + i % k];

@@ -36,6 +36,25 @@ def test_header_symbols_all_exported(lib):
         assert getattr(lib, name) is not None
 
 
+def test_fa2_header_symbols_all_exported(lib):
+    from svinet_b200 import fa2_engine
+    hdr = open(os.path.join(REPO, "include", "svi_fa2.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(svi_fa2_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(fa2_engine.FA2_SYMBOLS), declared ^ set(fa2_engine.FA2_SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    fa2_engine.bind(lib)
+    cfg = fa2_engine.Fa2Config()
+    lib.svi_fa2_default_config(C.byref(cfg), 100, 8)
+    assert (cfg.n, cfg.k, cfg.alpha, cfg.tau0, cfg.m_sets, cfg.online_iterations) == (100, 8, 0.125, 1025.0, 10, 50)
+    h = C.c_void_p()
+    assert lib.svi_fa2_create(None, C.byref(h)) == -1
+    cfg.k = 5000
+    assert lib.svi_fa2_create(C.byref(cfg), C.byref(h)) == -4
+    assert lib.svi_fa2_step(None, 0, 0, 0, 0, None) == -1
+
+
 def test_abi_version(lib):
     assert lib.svi_ls_abi_version() == 1
 
