@@ -70,6 +70,7 @@ bool Env::parse(int argc, char **argv) {
     else if (a == "-disjoint") disjoint = true;
     else if (a == "-adamic-adar") adamic_adar = true;
     else if (a == "-gpus") ngpus = atoi(next_arg(argc, argv, i));
+    else if (a == "-device-draw") device_draw = true;
     else if (a == "-dump-init") { dump_only = true; dump_dir = next_arg(argc, argv, i); }
     // -force, -online, -nodelay and anything unknown: accepted and ignored, like the reference
   }
@@ -78,7 +79,7 @@ bool Env::parse(int argc, char **argv) {
 }
 
 void Env::open_output() {
-  // n<N>-k<K>-<label>[-seed<S>]-linksampling   (src/env.hh:503-528)
+  // n<N>-k<K>-<label>[-seed<S>]-linksampling | -S..rnode   (src/env.hh:503-545)
   std::ostringstream sa;
   sa << "n" << n << "-" << "k" << k;
   if (label != "") {
@@ -89,7 +90,17 @@ void Env::open_output() {
     sa << "-" << q;
   }
   if (seed) sa << "-seed" << seed;
-  sa << "-linksampling";
+  if (link_sampling) {
+    sa << "-linksampling";
+  } else {
+    // stratified || delaylearn || nolambda || undirected || randomnode: undirected is always true
+    sa << "-";
+    if (stratified) sa << "S";
+    if (nolambda) sa << "P";
+    if (rpair) sa << "rpair";
+    if (rnode) sa << "rnode";
+    if (nonuniform) sa << "R";
+  }
   if (run_gap) sa << "-GAP";
   if (nthreads > 0) sa << "-T" << nthreads;
   if (itype > 0) sa << "-i" << itype;
@@ -169,13 +180,15 @@ void Env::plog(const std::string &key, const std::string &v) const { fprintf(plo
 
 void Env::usage() {
   fprintf(stdout,
-          "\nSVINET (B200 build): stochastic variational inference of undirected networks, link-sampling path\n"
+          "\nSVINET (B200 build): stochastic variational inference of undirected networks\n"
           "svinet [OPTIONS]\n"
           "\t-help\t\tusage\n\n"
           "\t-file <name>\tinput tab-separated file with a list of undirected links\n\n"
           "\t-n <N>\t\tnumber of nodes in network\n\n"
           "\t-k <K>\t\tnumber of communities\n\n"
-          "\t-link-sampling\tinference using link sampling (the only engine in this build)\n\n"
+          "\t-link-sampling\tinference using link sampling\n\n"
+          "\t-rnode -stratified\tinference using stratified random-node sampling (class FastAMM2)\n\n"
+          "\t-device-draw\t(with -rnode -stratified) minibatches are drawn on the GPU from a Philox stream\n\n"
           "\t-load-validation <fname>\tuse the pairs in the file as the validation set for convergence\n\n"
           "\t-load <dir/>\tresume from <dir/>gamma.txt and <dir/>lambda.txt\n\n"
           "\t-label\t\ttag output directory\n\n"

@@ -1,4 +1,4 @@
-// env.hh -- run configuration of the svinet drop-in CLI (link-sampling path only).
+// env.hh -- run configuration of the svinet drop-in CLI (-link-sampling and -rnode -stratified).
 //
 // Mirrors what the reference's Env carries for this path (reference src/env.hh:52-202,285-628 and the
 // argv loop src/main.cc:114-242): same flags, same defaults, same output-directory naming, same
@@ -47,6 +47,8 @@ struct Env {
   uint32_t nthreads = 0, itype = 0, scale = 1;
   bool nodelay = true, disjoint = false, adamic_adar = false;
   int ngpus = 1;                      // extension: -gpus N (ignored by the reference's parser)
+  bool device_draw = false;           // extension: -device-draw (with -rnode -stratified): the device draws the
+                                      //            minibatches from a Philox stream keyed by -seed (svi_fa2_run)
   bool dump_only = false;             // extension: -dump-init <dir> writes the start-up state and exits
   std::string dump_dir;               //            (host-logic tests; touches no GPU)
 
@@ -56,6 +58,10 @@ struct Env {
   double eta0 = 0, eta1 = 0;          // set by Network::set_env_variables (src/network.cc:223-250)
   double eta0_dense = 4700.59, eta1_dense = 0.77, eta0_sparse = 0.97, eta1_sparse = 6.33;
   double epsilon = 1e-30;             // src/env.hh:395
+  double meanchangethresh = 0.00001;  // src/env.hh:337  (the -rnode -stratified path, src/fastamm2.hh:194)
+  double tau0 = 1024, nodetau0 = 1024, nodekappa = 0.5, kappa = 0.9;   // src/env.hh:405-408
+  uint32_t online_iterations = 50;    // src/env.hh:415
+  bool deterministic = false;         // src/env.hh:446
   double precision_ratio = 0.001;
   bool undirected = true, nolambda = false;
   // effective values on this path (both members are never assigned in the reference)

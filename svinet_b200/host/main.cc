@@ -1,11 +1,12 @@
 // main.cc -- `svinet` command line, B200 build: the reference's CLI surface (src/main.cc:43-377) for the
-// one engine this repository re-implements, `-link-sampling`.  Every other mode of the reference is out
+// two engines this repository re-implements, `-link-sampling` and `-rnode -stratified`.  Every other mode is out
 // of scope and is refused with a message instead of being silently ignored.
 #include <csignal>
 #include <cstdio>
 #include <cstdlib>
 
 #include "env.hh"
+#include "fastamm2.hh"
 #include "linksampling.hh"
 #include "network.hh"
 
@@ -32,10 +33,12 @@ int main(int argc, char **argv) {
     Env::usage();
     exit(0);
   }
-  if (!env.link_sampling || env.gen || env.ppc || env.gml || env.findk || env.lcstats || env.orig) {
+  const bool fa2 = !env.link_sampling && env.stratified && env.rnode;       // src/main.cc:368
+  if ((!env.link_sampling && !fa2) || env.batch || env.massive || env.single || env.gen || env.ppc || env.gml ||
+      env.findk || env.lcstats || env.orig) {
     fprintf(stderr,
-            "svinet (B200 build): only -link-sampling is implemented here; the other engines and tools of the\n"
-            "reference (-batch, -rnode, -rpair, -infset, -single, -orig, -gen, -ppc, -gml, -findk) are unchanged\n"
+            "svinet (B200 build): -link-sampling and -rnode -stratified are implemented here; the other engines and\n"
+            "tools of the reference (-batch, -rpair, -infset, -single, -orig, -gen, -ppc, -gml, -findk) are unchanged\n"
             "upstream code and are not part of this build.\n");
     exit(-1);
   }
@@ -53,6 +56,15 @@ int main(int argc, char **argv) {
   }
   env.n = network.n() - network.singles();   // src/main.cc:291
 
+  if (fa2) {
+    FastAMM2 fastamm2(env, network);
+    if (env.dump_only) {
+      fastamm2.dump_init(env.dump_dir);
+      exit(0);
+    }
+    fastamm2.infer();
+    exit(0);
+  }
   LinkSampling ls(env, network);
   if (env.dump_only) {
     ls.dump_init(env.dump_dir);

@@ -1,9 +1,14 @@
 // rng.hh -- the random stream the reference consumes through GSL (src/linksampling.cc:71-75,392;
 // src/linksampling.hh:336-344): MT19937 with GSL's conventions (seed 0 -> 4357, uniform = x / 2^32,
 // uniform_int by rejection with scale = 0xffffffff / n).  Host-side only: on this path the generator is
-// used at start-up (held-out draw + gamma initialisation), never inside the iteration.
+// used at start-up (held-out draw + gamma initialisation), never inside the iteration.  The
+// -rnode -stratified path (fastamm2.cc) also draws its minibatches from it, one Bernoulli and one or two
+// uniform integers per iteration; the gamma variates follow the published Marsaglia-Tsang method with a
+// polar normal (upstream GSL's exact variate stream is not reproducible here: GSL is not vendored).
 #ifndef SVINET_B200_RNG_HH
 #define SVINET_B200_RNG_HH
+#include <cmath>
+#include <cstddef>
 #include <cstdint>
 
 class Mt19937 {
@@ -30,6 +35,45 @@ class Mt19937 {
     unsigned long k;
     do { k = next() / scale; } while (k >= n);
     return k;
+  }
+  // ---- variates the -rnode -stratified start-up consumes (src/fastamm2.cc:493,510,528,574) ----
+  double uniform_pos() {                       // gsl_rng_uniform_pos
+    double x;
+    do { x = uniform(); } while (x == 0);
+    return x;
+  }
+  unsigned bernoulli(double p) { return uniform() < p ? 1u : 0u; }   // gsl_ran_bernoulli
+  double gaussian() {                          // polar (Box-Muller) method, unit variance
+    double x, y, r2;
+    do {
+      x = -1 + 2 * uniform_pos();
+      y = -1 + 2 * uniform_pos();
+      r2 = x * x + y * y;
+    } while (r2 > 1.0 || r2 == 0);
+    return y * std::sqrt(-2.0 * std::log(r2) / r2);
+  }
+  double gamma(double a, double b) {           // gsl_ran_gamma: Marsaglia & Tsang (2000)
+    if (a < 1) {
+      const double u = uniform_pos();
+      return gamma(1.0 + a, b) * std::pow(u, 1.0 / a);
+    }
+    const double d = a - 1.0 / 3.0, c = (1.0 / 3.0) / std::sqrt(d);
+    double x, v, u;
+    for (;;) {
+      do { x = gaussian(); v = 1.0 + c * x; } while (v <= 0);
+      v = v * v * v;
+      u = uniform_pos();
+      if (u < 1 - 0.0331 * x * x * x * x) break;
+      if (std::log(u) < 0.5 * x * x + d * (1 - v + std::log(v))) break;
+    }
+    return b * d * v;
+  }
+  template <class T>
+  void shuffle(T *base, size_t n) {            // gsl_ran_shuffle: Fisher-Yates from the top
+    for (size_t i = n - 1; n && i > 0; i--) {
+      const size_t j = uniform_int(i + 1);
+      T t = base[i]; base[i] = base[j]; base[j] = t;
+    }
   }
 
  private:

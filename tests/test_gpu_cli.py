@@ -35,7 +35,7 @@ def run_case(cli, case, d):
 
 
 @pytest.mark.parametrize("case", ["c1_m30", "c1_natural", "c1_m1", "c1_seed7_m12", "c1_accuracy_m8", "c1_k7_m15",
-                                  "lfr_k28_m20", "c2_m12", "c2_m25"])
+                                  "lfr_k28_m20", "c2_m12", "c2_m25"])  # the -link-sampling fixtures
 def test_cli_output_directory_matches_reference(cli, case):
     with Scratch() as d:
         ent, out = run_case(cli, case, d)
@@ -57,6 +57,61 @@ def test_cli_output_directory_matches_reference(cli, case):
         assert noff <= max(2, nf // 1000), flips
         for f in ("infer.log", "logl.txt", "test-edges.txt", "network.dat"):
             assert os.path.lexists(os.path.join(out, f)), f
+
+
+FA2_CASES = [c for c in MANIFEST if MANIFEST[c].get("mode") == "-rnode -stratified"]
+
+
+@pytest.mark.parametrize("case", FA2_CASES)
+def test_fa2_cli_output_directory_matches_reference(cli, case):
+    """`svinet -rnode -stratified` (class FastAMM2): same flags as the fixture, host replays the reference's
+    mt19937 minibatch draws, the device runs every iteration."""
+    ent = MANIFEST[case]
+    with Scratch() as d:
+        inp = input_path(ent["input"], d)
+        local = os.path.join(d, ent["input"])
+        if not os.path.exists(local):
+            os.symlink(inp, local)
+        cmd = [cli, "-file", ent["input"], "-n", str(ent["n"]), "-k", str(ent["k"])] + ent["mode"].split() + ent["flags"]
+        p = subprocess.run(cmd, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=900)
+        assert p.returncode == 0, p.stderr.decode()
+        out = os.path.join(d, ent["outdir"])
+        flips = {}
+        for fname in ("gamma.txt", "lambda.txt", "groups.txt", "heldout.txt"):
+            got = open(os.path.join(out, fname)).read()
+            flips[fname] = compare_numeric_text(got, golden_text(case, fname), skip_cols=(1,) if fname == "heldout.txt" else ())
+        for fname in ("communities.txt", "communities_size.txt", "summary.txt", "heldout-pairs.txt", "param.txt"):
+            assert open(os.path.join(out, fname)).read() == golden_text(case, fname), fname
+        print(case, flips)
+        nf, noff = flips["gamma.txt"]
+        assert noff <= max(2, nf // 1000), flips
+        for f in ("infer.log", "cmap.txt", "precision.txt", "validation-pairs.txt", "mcount.txt", "aggregate.txt", "network.dat"):
+            assert os.path.lexists(os.path.join(out, f)), f
+
+
+def test_fa2_cli_device_draw(cli):
+    """-device-draw: minibatches from the device's Philox stream (svi_fa2_run); no reference fixture can exist
+    for it, so this checks the run end to end: the report cadence, finite positive state, rows that sum to 1."""
+    import numpy as np
+    ent = MANIFEST["fa2_lfr_k28_m300"]
+    with Scratch() as d:
+        inp = input_path(ent["input"], d)
+        if not os.path.exists(os.path.join(d, ent["input"])):
+            os.symlink(inp, os.path.join(d, ent["input"]))
+        cmd = [cli, "-file", ent["input"], "-n", "1000", "-k", "28", "-rnode", "-stratified", "-max-iterations", "250",
+               "-rfreq", "100", "-seed", "5", "-device-draw"]
+        p = subprocess.run(cmd, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=900)
+        assert p.returncode == 0, p.stderr.decode()
+        out = os.path.join(d, "n1000-k28-mmsb-seed5-Srnode")
+        rows = [l.split("\t") for l in open(os.path.join(out, "heldout.txt")).read().strip().split("\n")]
+        assert [r[0] for r in rows] == ["0", "100", "200"]
+        assert int(rows[2][-1]) > int(rows[1][-1]) > 0                      # pairs sampled keeps growing
+        gam = np.array([[float(x) for x in l.split("\t")[2:]] for l in open(os.path.join(out, "gamma.txt")).read().strip().split("\n")])
+        assert gam.shape == (1000, 28) and np.all(np.isfinite(gam)) and np.all(gam > 0)
+        grp = np.array([[float(x) for x in l.split("\t")[2:-1]] for l in open(os.path.join(out, "groups.txt")).read().strip().split("\n")])
+        assert np.allclose(grp.sum(axis=1), 1.0, atol=0.02)
+        # held-out likelihood of links improves over the initial state
+        assert float(rows[2][6]) > float(rows[0][6])
 
 
 def test_cli_resume_from_saved_model(cli):

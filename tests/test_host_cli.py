@@ -114,4 +114,39 @@ def test_ragged_input_selfloops_duplicates_and_single_nodes(cli):
 def test_cli_refuses_other_engines(cli):
     with Scratch() as d:
         p = subprocess.run([cli, "-file", "x", "-n", "5", "-k", "2", "-batch"], cwd=d, capture_output=True)
-        assert p.returncode != 0 and b"only -link-sampling" in p.stderr
+        assert p.returncode != 0 and b"are implemented here" in p.stderr
+
+
+# ---- -rnode -stratified (class FastAMM2) ------------------------------------------------------------
+@pytest.mark.parametrize("case", ["fa2_c1_m200", "fa2_c1_k6_seed9_m500", "fa2_lfr_k28_m300"])
+def test_fa2_startup_state_is_bit_identical_to_oracle(cli, case):
+    """shuffle_nodes, the held-out draw, init_gamma / init_lambda (fastamm2.cc:489-531) consume the same
+    mt19937 stream as the oracle (and, through its fixtures, the reference)."""
+    from test_oracle_fa2_golden import fa2_opts
+    ent = MANIFEST[case]
+    with Scratch() as d:
+        inp = input_path(ent["input"], d)
+        local = os.path.join(d, ent["input"])
+        if not os.path.exists(local):
+            os.symlink(inp, local)
+        dump = os.path.join(d, "dump"); os.makedirs(dump)
+        cmd = [cli, "-file", ent["input"], "-n", str(ent["n"]), "-k", str(ent["k"])] + ent["mode"].split() + \
+              ent["flags"] + ["-dump-init", dump]
+        subprocess.check_call(cmd, cwd=d, stdout=subprocess.DEVNULL)
+        k = ent["k"]
+        g = orc.Graph.read(inp, ent["n"])
+        m = orc.Fa2Model(g, k, **fa2_opts(ent["flags"]))
+        assert np.array_equal(np.fromfile(os.path.join(dump, "gamma.f64")).reshape(-1, k), m.gamma)
+        assert np.array_equal(np.fromfile(os.path.join(dump, "lambda.f64")).reshape(k, 2), m.lambda_)
+        assert np.array_equal(np.fromfile(os.path.join(dump, "shuffled.u32"), dtype=np.uint32), m.shuffled)
+        assert np.array_equal(np.fromfile(os.path.join(dump, "heldout.u32"), dtype=np.uint32).reshape(-1, 2),
+                              m.heldout_pairs(sorted_=False))
+        out = os.path.join(d, ent["outdir"])
+        assert open(os.path.join(out, "heldout-pairs.txt")).read() == golden_text(case, "heldout-pairs.txt")
+        want = golden_text(case, "param.txt").split("\n")
+        have = [l for l in open(os.path.join(out, "param.txt")).read().split("\n")]
+        while have and not have[-1]:
+            have.pop()
+        # everything the constructor logs, i.e. all but the final "maxiterations reached" line
+        assert have == want[:len(have)] and len(have) >= 60, (have[-3:], want[len(have) - 3:len(have)])
+        m.close(); g.close()
