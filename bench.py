@@ -6,10 +6,12 @@
 One "step" = one full variational iteration (phi sweep + mean indicators + s3 sweep + lambda finish +
 expectation refresh + prune == the loop body src/linksampling.cc:584-761) over ALL training links of the
 workload.  `value` = links x steps / device time, state resident in HBM.  `e2e` = the same step driven
-through the C ABI with HOST buffers: every step uploads gamma/lambda from pinned memory
-(svi_ls_set_state), runs svi_ls_step, evaluates the held-out likelihood (svi_ls_heldout, the "loss" the
-reference computes every iteration, src/linksampling.cc:778-780) and downloads gamma/lambda
-(svi_ls_get_state).
+through the C ABI with HOST buffers the way the reference-facing caller drives it every iteration:
+svi_ls_step, the held-out likelihood (svi_ls_heldout: host pair lists in, host log-likelihoods out -- the
+"loss" the reference computes every iteration, src/linksampling.cc:778-780) and the link-community
+membership of the sweep (svi_ls_get_membership, host bits out; log_communities, :785).
+`e2e.state_roundtrip` is the pessimistic variant that also uploads and downloads the whole gamma/lambda
+state around every step (svi_ls_set_state / svi_ls_get_state).
 
 Under torchrun (N > 1) every rank owns an edge-balanced node block (svinet_b200/sharded.py); timing is
 CUDA events on the launching stream, max over ranks.
@@ -166,6 +168,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout must carry exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes there
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     n, k, target = WORKLOADS[args.workload]
@@ -233,20 +238,41 @@ def run_ours(args):
         total_ms = float(t.item())
     value = nlinks * args.steps / (total_ms * 1e-3)
 
-    # ---- end-to-end through the C ABI with host buffers (rank-local state up + down every step) ----
+    # ---- end-to-end through the C ABI with HOST buffers -------------------------------------------------
+    # What the reference-facing caller (svinet_b200/host/linksampling.cc::infer, the drop-in for
+    # src/linksampling.cc:571-789 with its default reportfreq = 1) does every iteration: svi_ls_step, then the
+    # held-out likelihood of the validation pairs (pair lists host -> device, log-likelihoods device -> host,
+    # src/linksampling.cc:778-780) and the link-community membership of the sweep (device -> host,
+    # log_communities :785).  The graph and the variational state stay resident, as they do in that caller.
+    # `state_roundtrip` additionally re-uploads and downloads the WHOLE state (gamma, lambda) around every
+    # step -- a pattern no caller has, kept as the pessimistic bound the previous profiles quoted.
     e2e = None
     if world == 1:
         pin_g = torch.empty((n, k), dtype=torch.float64).pin_memory()
         pin_l = torch.empty((k, 2), dtype=torch.float64).pin_memory()
         eng.get_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
         hp, hq, hy = heldout_pairs(n, links, max(2, min(nlinks // 100, 2_000_000)))
-        e2e_steps = max(1, min(args.steps, 5))
-        for w in range(1):
-            eng.set_state_ptr(pin_g.data_ptr(), pin_l.data_ptr()); eng.step(it, True, True)
-            eng.heldout(hp, hq, hy); eng.get_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
+        e2e_steps = max(1, min(args.steps, 10))
+        eng.step(it, True, True); it += 1
+        eng.heldout(hp, hq, hy); bits = eng.membership_bits()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for s in range(e2e_steps):
+            eng.step(it, True, True); it += 1
+            ll = eng.heldout(hp, hq, hy)
+            bits = eng.membership_bits()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": nlinks * e2e_steps / dt, "unit": UNIT, "steps": e2e_steps,
+               "h2d_bytes_per_step": hp.nbytes + hq.nbytes + hy.nbytes,
+               "d2h_bytes_per_step": ll.nbytes + bits.nbytes,
+               "what": "per iteration, as the drop-in CLI does: svi_ls_step + svi_ls_heldout(host pairs -> host "
+                       "log-likelihoods) + svi_ls_get_membership(host bits); graph and state resident",
+               "heldout_mean_loglik": float(ll.mean())}
+        rt_steps = max(1, min(args.steps, 5))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(rt_steps):
             eng.set_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
             eng.step(it, True, True); it += 1
             ll = eng.heldout(hp, hq, hy)
@@ -254,14 +280,15 @@ def run_ours(args):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         state_bytes = (n * k + 2 * k) * 8
-        e2e = {"value": nlinks * e2e_steps / dt, "unit": UNIT, "steps": e2e_steps,
-               "h2d_bytes_per_step": state_bytes + hp.nbytes + hq.nbytes + hy.nbytes,
-               "d2h_bytes_per_step": state_bytes + ll.nbytes,
-               "what": "svi_ls_set_state(pinned host) + svi_ls_step + svi_ls_heldout + svi_ls_get_state(pinned host)",
-               "heldout_mean_loglik": float(ll.mean())}
+        e2e["state_roundtrip"] = {
+            "value": nlinks * rt_steps / dt, "unit": UNIT, "steps": rt_steps,
+            "h2d_bytes_per_step": state_bytes + hp.nbytes + hq.nbytes + hy.nbytes,
+            "d2h_bytes_per_step": state_bytes + ll.nbytes,
+            "what": "svi_ls_set_state(pinned host) + svi_ls_step + svi_ls_heldout + svi_ls_get_state(pinned host)"}
         del pin_g, pin_l
     else:
-        e2e = runner.e2e(step_fn=step, it0=it, steps=max(1, min(args.steps, 5)), nlinks=nlinks, unit=UNIT)
+        e2e = runner.e2e(step_fn=step, it0=it, steps=max(1, min(args.steps, 5)), nlinks=nlinks, unit=UNIT,
+                         heldout=heldout_pairs(n, links, max(2, min(nlinks // 100, 2_000_000))))
 
     if rank != 0:
         if world > 1:

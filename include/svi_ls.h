@@ -120,7 +120,7 @@ int svi_ls_get_kvectors(svi_ls *h, double *sum, double *s1, double *s2, double *
  *   phase_node  : mean indicators for the shard's rows             -> SVI_BUF_MPHI rows, local
  *                 column sums in SVI_BUF_KVEC (sum,s1,s2)            [all-reduce sum,s1,s2;
  *                                                                     all-gather mphi rows]
- *   phase_s3    : s3 over the shard's (p<q) half-edges             -> SVI_BUF_KVEC (s3) [all-reduce]
+ *   phase_s3    : s3 over the links the shard's nodes own          -> SVI_BUF_KVEC (s3) [all-reduce]
  *   phase_finish: lambda, Elogbeta, gamma rescale, Elogpi, prune   -> SVI_BUF_EXPPI rows,
  *                 SVI_BUF_CONVERGED                                  [all-gather both] */
 int svi_ls_phase_phi(svi_ls *h, uint32_t iter, int write_comm);

@@ -108,6 +108,8 @@ struct svi_fa2 {
   uint32_t *d_pairs = nullptr, *d_shuffled = nullptr, *d_adj = nullptr;
   uint64_t *d_adj_off = nullptr, *d_heldout = nullptr;
   uint8_t *d_touched = nullptr;
+  uint32_t *d_ballots = nullptr, *d_counts = nullptr;   // draw window: 32 ballots + 1 count per block
+  uint32_t draw_blocks = 0;
   Fa2Ctrl *d_ctrl = nullptr;
   size_t stage_bytes = 0;
   Fa2Ctrl *h_ctrl = nullptr;   // pinned staging for step()
@@ -149,6 +151,14 @@ int ensure_pairs(svi_fa2 *h, uint64_t npairs) {
   h->P.pairs = h->d_pairs;
   h->P.cap_pairs = (uint32_t)cap;
   return SVI_OK;
+}
+
+// the three launches of one device-side minibatch draw (svi_fa2_kernels.cuh)
+void launch_draw(svi_fa2 *h, uint32_t iter, uint64_t seed) {
+  const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
+  svi::k_fa2_draw_count<<<h->draw_blocks, 1024, 0, h->stream>>>(h->P, iter, lo, hi, h->d_ballots, h->d_counts);
+  svi::k_fa2_draw_emit<<<h->draw_blocks, 1024, 0, h->stream>>>(h->P, iter, lo, hi, h->d_ballots, h->d_counts, h->draw_blocks);
+  svi::k_fa2_draw_tail<<<1, 1024, 0, h->stream>>>(h->P, iter, lo, hi, h->draw_blocks);
 }
 
 void launch_iteration(svi_fa2 *h) {
@@ -238,7 +248,8 @@ void svi_fa2_destroy(svi_fa2 *h) {
   DevGuard guard(h->device);
   cudaStreamSynchronize(h->stream);
   void *ptrs[] = {h->d_gamma, h->d_lambda, h->d_elogbeta, h->d_elogf, h->d_epi, h->d_partS, h->d_partL, h->d_stage,
-                  h->d_pairs, h->d_shuffled, h->d_adj, h->d_adj_off, h->d_heldout, h->d_touched, h->d_ctrl};
+                  h->d_pairs, h->d_shuffled, h->d_adj, h->d_adj_off, h->d_heldout, h->d_touched, h->d_ctrl,
+                  h->d_ballots, h->d_counts};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -393,6 +404,16 @@ int svi_fa2_set_graph(svi_fa2 *h, uint64_t nlinks, const uint32_t *links, uint64
   const uint32_t setsize = (uint32_t)((double)n / (double)h->cfg.m_sets);
   int rc = ensure_pairs(h, std::max<uint64_t>(maxdeg, setsize));
   if (rc) return rc;
+  // draw window: the set size plus everything a typical start node excludes (its links, itself, held-out
+  // partners) plus slack; a start node that excludes more is finished by k_fa2_draw_tail
+  uint64_t avgdeg = n ? 2 * nlinks / n : 0;
+  uint64_t window = std::max<uint64_t>(setsize + 4 * avgdeg + 2048, std::min<uint64_t>(maxdeg, 1u << 20));
+  window = std::min<uint64_t>(window, std::max<uint64_t>(n, maxdeg));
+  h->draw_blocks = (uint32_t)((window + 1023) / 1024);
+  for (void **p : {(void **)&h->d_ballots, (void **)&h->d_counts})
+    if (*p) { cudaFree(*p); *p = nullptr; }
+  SVI_CK(dalloc(h, &h->d_ballots, (size_t)h->draw_blocks * 32));
+  SVI_CK(dalloc(h, &h->d_counts, h->draw_blocks));
   h->have_graph = true;
   return SVI_OK;
 }
@@ -408,7 +429,7 @@ int svi_fa2_run(svi_fa2 *h, uint32_t iter0, uint32_t iters, uint64_t seed, uint6
     before = h->h_ctrl->total_sampled;
   }
   for (uint32_t i = 0; i < iters; ++i) {
-    svi::k_fa2_draw<<<1, 1024, 0, h->stream>>>(h->P, iter0 + i, (uint32_t)seed, (uint32_t)(seed >> 32));
+    launch_draw(h, iter0 + i, seed);
     launch_iteration(h);
   }
   h->nodec += iters;
@@ -426,7 +447,7 @@ int svi_fa2_draw(svi_fa2 *h, uint32_t iter, uint64_t seed, uint32_t *type, uint3
   if (!h) return fail(SVI_ERR_INVALID, "null handle");
   if (!h->have_graph) return fail(SVI_ERR_INVALID, "svi_fa2_draw: call svi_fa2_set_graph first");
   DevGuard guard(h->device);
-  svi::k_fa2_draw<<<1, 1024, 0, h->stream>>>(h->P, iter, (uint32_t)seed, (uint32_t)(seed >> 32));
+  launch_draw(h, iter, seed);
   SVI_CK(cudaGetLastError());
   SVI_CK(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(Fa2Ctrl), cudaMemcpyDeviceToHost, h->stream));
   SVI_CK(cudaStreamSynchronize(h->stream));
@@ -495,7 +516,7 @@ int svi_fa2_get_info(svi_fa2 *h, svi_fa2_info *info) {
   info->ld = h->P.ld; info->lanes = (uint32_t)h->ops.lanes; info->vec = (uint32_t)h->ops.vec;
   info->pair_blocks = h->P.pair_blocks; info->device_bytes = h->device_bytes;
   info->last_npairs = c.npairs; info->last_rounds = c.last_rounds;
-  info->kernels_per_step = 4;
+  info->kernels_per_step = h->have_graph ? 7 : 4;   // 3 draw launches + prep, pairs, blend, lambda
   return SVI_OK;
 }
 

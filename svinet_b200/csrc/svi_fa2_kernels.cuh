@@ -18,7 +18,7 @@
 //   k_fa2_blend  every other row: decay towards alpha (the bandwidth-bound pass, 2 x N x K x 8 bytes);
 //                the start row gets the reduced partials
 //   k_fa2_lambda one block: reduce the phi1*phi2 partials, blend lambda, advance the node counter
-//   k_fa2_draw   one block: the minibatch itself, from a Philox4x32-10 stream keyed by (seed, iter)
+//   k_fa2_draw_* the minibatch itself, from a Philox4x32-10 stream keyed by (seed, iter)
 #pragma once
 #include "svi_ls_kernels.cuh"
 
@@ -354,78 +354,152 @@ __device__ __forceinline__ bool fa2_is_heldout(const Fa2Params &P, uint32_t a, u
   return false;
 }
 
-// One block.  Order-preserving compaction of the candidates (block scan per chunk of blockDim.x):
+// The draw runs as three launches so that the candidate tests (binary searches in the start node's
+// adjacency and in the held-out set: dependent global loads) spread over many blocks:
+//   k_fa2_draw_count : decide (type, start, first candidate) from the Philox stream; every block tests its
+//                      1024 candidates of the WINDOW, keeps the validity ballots and its count
+//   k_fa2_draw_emit  : block prefix over the counts, order-preserving write of the first `want` valid pairs,
+//                      control block
+//   k_fa2_draw_tail  : one block, only when the window held fewer than `want` valid candidates (a start
+//                      node with more excluded partners than the window's slack): continues serially
+// Sampling rules:
 //   type 0: the start node's neighbours minus held-out pairs                  (src/fastamm2.cc:943-960)
 //   type 1: walk the shuffled node order from a random block boundary, keep non-links that are not held
 //           out, until n/m nodes are collected                                (src/fastamm2.cc:1095-1125)
-static __global__ void __launch_bounds__(1024) k_fa2_draw(const Fa2Params P, uint32_t iter, uint32_t seed_lo, uint32_t seed_hi) {
-  __shared__ uint32_t warp_tot[32];
-  __shared__ uint32_t s_base, s_done;
+struct Fa2Draw {
+  uint32_t type, start, q0, want;
+  uint64_t ncand;          // candidates available (type 0: degree; type 1: one lap = n)
+};
+
+__device__ __forceinline__ Fa2Draw fa2_draw_header(const Fa2Params &P, uint32_t iter, uint32_t seed_lo, uint32_t seed_hi) {
   uint32_t r[4] = {iter, 0u, 0u, 0u};
   philox4x32_10(r, seed_lo, seed_hi);
-  const uint32_t type = (double)r[0] * (1.0 / 4294967296.0) < P.inf_epsilon ? 1u : 0u;   // gsl_ran_bernoulli
-  const uint32_t start = __umulhi(r[1], P.n);
+  Fa2Draw d;
+  d.type = (double)r[0] * (1.0 / 4294967296.0) < P.inf_epsilon ? 1u : 0u;   // gsl_ran_bernoulli
+  d.start = __umulhi(r[1], P.n);
   const uint32_t setsize = (uint32_t)((double)P.n / (double)P.m_sets);
-  const uint32_t lanei = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { s_base = 0; s_done = 0; }
-  __syncthreads();
-  uint64_t ncand;
-  uint32_t q0 = 0, want;
-  if (type == 0) {
-    ncand = P.adj_off[start + 1] - P.adj_off[start];
-    want = 0xffffffffu;
+  if (d.type == 0) {
+    d.q0 = 0;
+    d.ncand = P.adj_off[d.start + 1] - P.adj_off[d.start];
+    d.want = 0xffffffffu;
   } else {
-    q0 = setsize ? (__umulhi(r[2], P.n) / setsize) * setsize : 0u;
-    ncand = P.n;          // at most one lap over the shuffled order
-    want = setsize;
+    d.q0 = setsize ? (__umulhi(r[2], P.n) / setsize) * setsize : 0u;
+    d.ncand = P.n;
+    d.want = setsize;
   }
-  for (uint64_t c0 = 0; c0 < ncand; c0 += blockDim.x) {
-    const uint64_t ci = c0 + threadIdx.x;
+  return d;
+}
+
+__device__ __forceinline__ bool fa2_candidate(const Fa2Params &P, const Fa2Draw &d, uint64_t ci, uint32_t *node) {
+  if (ci >= d.ncand) return false;
+  if (d.type == 0) {
+    *node = P.adj[P.adj_off[d.start] + ci];
+    return !fa2_is_heldout(P, d.start, *node);
+  }
+  *node = P.shuffled[(d.q0 + ci) % P.n];
+  return *node != d.start && !fa2_is_link(P, d.start, *node) && !fa2_is_heldout(P, d.start, *node);
+}
+
+// window of block b: candidates [b*1024, (b+1)*1024)
+static __global__ void __launch_bounds__(1024) k_fa2_draw_count(const Fa2Params P, uint32_t iter, uint32_t seed_lo,
+                                                                uint32_t seed_hi, uint32_t *ballots, uint32_t *counts) {
+  __shared__ uint32_t warp_tot[32];
+  const Fa2Draw d = fa2_draw_header(P, iter, seed_lo, seed_hi);
+  const uint32_t lanei = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint64_t ci = (uint64_t)blockIdx.x * 1024u + threadIdx.x;
+  uint32_t node = 0;
+  const bool ok = fa2_candidate(P, d, ci, &node);
+  const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+  if (lanei == 0) {
+    ballots[blockIdx.x * 32u + warp] = bal;
+    warp_tot[warp] = __popc(bal);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 32; ++w) t += warp_tot[w];
+    counts[blockIdx.x] = t;
+  }
+}
+
+static __global__ void __launch_bounds__(1024) k_fa2_draw_emit(const Fa2Params P, uint32_t iter, uint32_t seed_lo,
+                                                               uint32_t seed_hi, const uint32_t *ballots,
+                                                               const uint32_t *counts, uint32_t nblocks) {
+  __shared__ uint32_t s_prefix;
+  const Fa2Draw d = fa2_draw_header(P, iter, seed_lo, seed_hi);
+  const uint32_t lanei = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (warp == 0) {   // valid candidates in the blocks before this one
+    uint32_t t = 0;
+    for (uint32_t b = lanei; b < blockIdx.x; b += 32) t += counts[b];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lanei == 0) s_prefix = t;
+  }
+  __syncthreads();
+  uint32_t pos = s_prefix;
+  for (uint32_t w = 0; w < warp; ++w) pos += __popc(ballots[blockIdx.x * 32u + w]);
+  const uint32_t bal = ballots[blockIdx.x * 32u + warp];
+  pos += __popc(bal & ((1u << lanei) - 1u));
+  if (((bal >> lanei) & 1u) && pos < d.want && pos < P.cap_pairs) {
+    const uint64_t ci = (uint64_t)blockIdx.x * 1024u + threadIdx.x;
+    const uint32_t node = d.type == 0 ? P.adj[P.adj_off[d.start] + ci] : P.shuffled[(d.q0 + ci) % P.n];
+    P.pairs[2 * pos] = min(d.start, node);
+    P.pairs[2 * pos + 1] = max(d.start, node);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    uint32_t tot = 0;
+    for (uint32_t b = 0; b < nblocks; ++b) tot += counts[b];
+    Fa2Ctrl *w = P.ctrl;
+    const uint32_t np = min(min(tot, d.want), P.cap_pairs);
+    w->type = d.type;
+    w->start = d.start;
+    w->npairs = np;          // k_fa2_draw_tail may still raise it
+    w->iter = iter;
+    w->sampled_inc = d.type == 0 ? d.ncand : np;
+    w->last_rounds = 0;
+    w->rho_node = pow(P.nodetau0 + w->nodec, -1.0 * P.nodekappa);              // :606
+    w->rho_t = pow(P.tau0 + ((double)iter + 1.0), -1.0 * P.kappa);             // :627, _lambda_start_iter = 0
+    w->scale = d.type == 0 ? (double)P.n / (2.0 * (1.0 - P.inf_epsilon))       // :591-592
+                           : ((double)P.n * (double)P.m_sets) / (2.0 * P.inf_epsilon);
+  }
+}
+
+// serial continuation past the window (rare): same chunked block scan as a single-block draw
+static __global__ void __launch_bounds__(1024) k_fa2_draw_tail(const Fa2Params P, uint32_t iter, uint32_t seed_lo,
+                                                               uint32_t seed_hi, uint32_t nblocks) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t s_base, s_done;
+  const Fa2Draw d = fa2_draw_header(P, iter, seed_lo, seed_hi);
+  const uint64_t window = (uint64_t)nblocks * 1024u;
+  if (P.ctrl->npairs >= d.want || window >= d.ncand) return;   // the window sufficed (uniform across the block)
+  const uint32_t lanei = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_base = P.ctrl->npairs; s_done = 0; }
+  __syncthreads();
+  for (uint64_t c0 = window; c0 < d.ncand; c0 += 1024u) {
     uint32_t node = 0;
-    bool ok = false;
-    if (ci < ncand) {
-      if (type == 0) {
-        node = P.adj[P.adj_off[start] + ci];
-        ok = !fa2_is_heldout(P, start, node);
-      } else {
-        node = P.shuffled[(q0 + ci) % P.n];
-        ok = node != start && !fa2_is_link(P, start, node) && !fa2_is_heldout(P, start, node);
-      }
-    }
+    const bool ok = fa2_candidate(P, d, c0 + threadIdx.x, &node);
     const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-    const uint32_t before = __popc(bal & ((1u << lanei) - 1u));
     if (lanei == 0) warp_tot[warp] = __popc(bal);
     __syncthreads();
-    uint32_t off = s_base;
-    for (uint32_t w = 0; w < warp; ++w) off += warp_tot[w];
-    const uint32_t pos = off + before;
-    if (ok && pos < want && pos < P.cap_pairs) {
-      P.pairs[2 * pos] = min(start, node);
-      P.pairs[2 * pos + 1] = max(start, node);
+    uint32_t pos = s_base + __popc(bal & ((1u << lanei) - 1u));
+    for (uint32_t w = 0; w < warp; ++w) pos += warp_tot[w];
+    if (ok && pos < d.want && pos < P.cap_pairs) {
+      P.pairs[2 * pos] = min(d.start, node);
+      P.pairs[2 * pos + 1] = max(d.start, node);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       uint32_t tot = 0;
-      for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) tot += warp_tot[w];
+      for (int w = 0; w < 32; ++w) tot += warp_tot[w];
       s_base += tot;
-      if (s_base >= want) s_done = 1;
+      if (s_base >= d.want) s_done = 1;
     }
     __syncthreads();
     if (s_done) break;
   }
   if (threadIdx.x == 0) {
-    Fa2Ctrl *w = P.ctrl;
-    const uint32_t np = min(min(s_base, want), P.cap_pairs);
-    w->type = type;
-    w->start = start;
-    w->npairs = np;
-    w->iter = iter;
-    w->sampled_inc = type == 0 ? ncand : np;
-    w->last_rounds = 0;
-    w->rho_node = pow(P.nodetau0 + w->nodec, -1.0 * P.nodekappa);              // :606
-    w->rho_t = pow(P.tau0 + ((double)iter + 1.0), -1.0 * P.kappa);             // :627, _lambda_start_iter = 0
-    w->scale = type == 0 ? (double)P.n / (2.0 * (1.0 - P.inf_epsilon))         // :591-592
-                         : ((double)P.n * (double)P.m_sets) / (2.0 * P.inf_epsilon);
+    const uint32_t np = min(min(s_base, d.want), P.cap_pairs);
+    P.ctrl->npairs = np;
+    if (d.type == 1) P.ctrl->sampled_inc = np;
   }
 }
 

@@ -295,6 +295,15 @@ int ensure_stage(svi_ls *h, size_t elems) {
   return SVI_OK;
 }
 
+// Which endpoint sweeps a link in the s3 pass.  The pass is symmetric in its endpoints (src/linksampling.cc:
+// 731-746: the full product commutes, and the shortcut always reads "the other endpoint's row at the converged
+// endpoint's community"), so any rule works; the parity rule gives every contiguous node block about half of
+// its links, whereas "the smaller id owns" hands the low blocks of a sharded run most of the s3 work.
+inline uint32_t s3_owner(uint32_t p, uint32_t q) {
+  const uint32_t lo = std::min(p, q), hi = std::max(p, q);
+  return ((lo ^ hi) & 1u) ? lo : hi;
+}
+
 // balanced split of `deg` neighbours into chunks of at most seg_len
 inline void push_segments(uint32_t node, uint32_t beg, uint32_t deg, uint32_t seg_len, std::vector<uint32_t> &sn,
                           std::vector<uint32_t> &sb, std::vector<uint32_t> &sc) {
@@ -351,7 +360,7 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   const uint32_t nlocal = ne - nb, ld = (k + 3u) & ~3u, words = (k + 31u) / 32u;
   h->nlocal = nlocal;
 
-  // ---- CSR of the shard's half-edges; lower neighbours first, upper (q > p) last ----
+  // ---- CSR of the shard's half-edges; the neighbours a node OWNS for the s3 sweep are stored last ----
   std::vector<uint32_t> deg_lo(nlocal, 0), deg_up(nlocal, 0);
   std::vector<double> tl_host(n, 0.0);
   for (uint64_t e = 0; e < cfg->nlinks; ++e) {
@@ -360,11 +369,11 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
       delete h;
       return fail(SVI_ERR_INVALID, "svi_ls_create: link %llu = (%u,%u) out of range", (unsigned long long)e, p, q);
     }
-    const uint32_t lo = std::min(p, q), hi = std::max(p, q);
-    if (lo >= nb && lo < ne) deg_up[lo - nb]++;
-    if (hi >= nb && hi < ne) deg_lo[hi - nb]++;
-    tl_host[lo] += 2.0;   // Q3: both adjacency directions count each link for both endpoints
-    tl_host[hi] += 2.0;
+    const uint32_t own = s3_owner(p, q), oth = own == p ? q : p;
+    if (own >= nb && own < ne) deg_up[own - nb]++;
+    if (oth >= nb && oth < ne) deg_lo[oth - nb]++;
+    tl_host[p] += 2.0;   // Q3: both adjacency directions count each link for both endpoints
+    tl_host[q] += 2.0;
   }
   if (tl) std::copy(tl, tl + n, tl_host.begin());
   std::vector<uint64_t> off(nlocal + 1, 0);
@@ -384,9 +393,9 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
     }
     for (uint64_t e = 0; e < cfg->nlinks; ++e) {
       const uint32_t p = links[2 * e], q = links[2 * e + 1];
-      const uint32_t lo = std::min(p, q), hi = std::max(p, q);
-      if (lo >= nb && lo < ne) col[cur_up[lo - nb]++] = hi;
-      if (hi >= nb && hi < ne) col[cur_lo[hi - nb]++] = lo;
+      const uint32_t own = s3_owner(p, q), oth = own == p ? q : p;
+      if (own >= nb && own < ne) col[cur_up[own - nb]++] = oth;
+      if (oth >= nb && oth < ne) col[cur_lo[oth - nb]++] = own;
     }
   }
   uint64_t he3 = 0;

@@ -151,33 +151,33 @@ class ShardedLinkSampling:
         import numpy as _np
         return [float(_np.mean([e[i].elapsed_time(e[i + 1]) for e in ev])) for i in range(4)]
 
-    def e2e(self, step_fn, it0, steps, nlinks, unit):
-        """Same step driven with HOST state: every step each rank uploads the full gamma/lambda from pinned
-        memory (svi_ls_set_state), runs the sharded iteration, and downloads gamma/lambda
-        (svi_ls_get_state after the row all-gather)."""
+    def e2e(self, step_fn, it0, steps, nlinks, unit, heldout=None):
+        """The step driven the way a reference-facing caller drives it, with HOST buffers every iteration: the
+        sharded iteration, a gamma row all-gather, the held-out likelihood of this rank's slice of the
+        validation pairs (host pair lists in, host log-likelihoods out) and the link-community membership bits
+        (device -> host).  Bytes are per rank."""
         import time
-        n, k = self.n, self.k
-        pin_g = torch.empty((n, k), dtype=torch.float64).pin_memory()
-        pin_l = torch.empty((k, 2), dtype=torch.float64).pin_memory()
-        self._allgather_rows("gamma")
-        self.eng.get_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
+        hp, hq, hy = heldout if heldout is not None else (np.zeros(0, np.uint32),) * 2 + (np.zeros(0, np.uint8),)
+        sl = slice(self.rank, None, self.world)
+        hp, hq, hy = np.ascontiguousarray(hp[sl]), np.ascontiguousarray(hq[sl]), np.ascontiguousarray(hy[sl])
         it = it0
+        ll = bits = np.zeros(0)
         for timed in (False, True):
             dist.barrier(group=self.group)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(1 if not timed else steps):
-                self.eng.set_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
                 step_fn(it)
                 it += 1
                 self._allgather_rows("gamma")
-                self.eng.get_state_ptr(pin_g.data_ptr(), pin_l.data_ptr())
+                ll = self.eng.heldout(hp, hq, hy)
+                bits = self.eng.membership_bits()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-        state_bytes = (n * k + 2 * k) * 8
         return {"value": nlinks * steps / float(t.item()), "unit": unit, "steps": steps,
-                "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
-                "what": "per rank: svi_ls_set_state(pinned host) + sharded step (NCCL exchanges) + gamma row "
-                        "all-gather + svi_ls_get_state(pinned host); bytes are per rank"}
+                "h2d_bytes_per_step": int(hp.nbytes + hq.nbytes + hy.nbytes),
+                "d2h_bytes_per_step": int(ll.nbytes + bits.nbytes),
+                "what": "per rank and iteration: sharded step (NCCL exchanges) + gamma row all-gather + "
+                        "svi_ls_heldout on 1/world of the pairs (host in/out) + svi_ls_get_membership (host bits)"}
