@@ -301,7 +301,7 @@ int FastAMM2::load_model() {
 
 void FastAMM2::plan_links(std::vector<uint32_t> &pairs) {
   start_node_ = (uint32_t)rng_.uniform_int(n_);                  // :936
-  const std::vector<uint32_t> &edges = net_.get_edges(start_node_);
+  const NeighbourSpan edges = net_.get_edges(start_node_);
   total_pairs_sampled_ += edges.size();                          // :950
   for (uint32_t a : edges) {
     Edge e(start_node_, a);

@@ -150,3 +150,30 @@ def test_fa2_startup_state_is_bit_identical_to_oracle(cli, case):
         # everything the constructor logs, i.e. all but the final "maxiterations reached" line
         assert have == want[:len(have)] and len(have) >= 60, (have[-3:], want[len(have) - 3:len(have)])
         m.close(); g.close()
+
+
+def test_ingest_sort_dedup_matches_oracle_on_messy_input(cli):
+    """The sort-based duplicate removal and the flat / hashed id tables keep the reference's semantics: first
+    occurrence wins, either direction counts as a repeat, first-appearance sequence ids, insertion-ordered
+    adjacency (oracle graph == reference Network::read, pinned by the fixtures)."""
+    rng = np.random.default_rng(12)
+    n_ids = 300
+    ids = np.concatenate([rng.integers(0, 5000, n_ids - 20), rng.integers(3_000_000_000, 4_000_000_000, 20)])
+    a = ids[rng.integers(0, n_ids, 6000)]
+    b = ids[rng.integers(0, n_ids, 6000)]
+    with Scratch() as d:
+        with open(os.path.join(d, "g.txt"), "w") as f:
+            for x, y in zip(a, b):
+                f.write("%d%s%d\n" % (x, "\t" if (x + y) % 3 else " ", y))
+        n_distinct = len(np.unique(np.concatenate([a, b])))
+        for n_arg in (n_distinct, n_distinct + 7, n_distinct - 25):      # exact, padded with singles, too small
+            dump = os.path.join(d, "dump%d" % n_arg); os.makedirs(dump)
+            subprocess.check_call([cli, "-file", "g.txt", "-n", str(n_arg), "-k", "3", "-link-sampling", "-accuracy",
+                                   "-label", "t%d" % n_arg, "-dump-init", dump], cwd=d, stdout=subprocess.DEVNULL)
+            links = np.fromfile(os.path.join(dump, "links.u32"), dtype=np.uint32).reshape(-1, 2)
+            gamma = np.fromfile(os.path.join(dump, "gamma.f64")).reshape(-1, 3)
+            g = orc.Graph.read(os.path.join(d, "g.txt"), n_arg)
+            m = orc.Model(g, 3, accuracy=1)
+            assert links.shape[0] == g.ones
+            assert np.array_equal(links, m.state.arr("links")) and np.array_equal(gamma, m.state.arr("gamma"))
+            m.close(); g.close()
