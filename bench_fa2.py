@@ -7,9 +7,11 @@ bench.py (the driver's contract) measures the headline `-link-sampling` path; th
 path of SURVEY.md section 8 (rows a9-a11, f4) the same way.  One "step" = one iteration of FastAMM2::infer
 (src/fastamm2.cc:566-640): minibatch draw (device Philox stream, svi_fa2_run), per-pair two-phi coordinate
 ascent, Robbins-Monro blend of ALL N gamma rows and of lambda.  Reported: iterations/s, pair-updates/s
-(pairs x iterations / device time), mean coordinate-ascent rounds per pair, and the roofline of the blend
-(the bandwidth-bound kernel: it reads and writes every gamma row, 2 x N x ld x 8 bytes per iteration; timed
-as a step with an empty minibatch, i.e. prep + an idle pair kernel + the blend + the lambda kernel).
+(pairs x iterations / device time), mean coordinate-ascent rounds per pair.  The default handle carries the
+decay of the untouched rows as one scalar (lazy mode); a second handle with eager_blend = 1 runs the
+reference's explicit pass and gives `eager_blend_ms_per_step` and the roofline of that blend (the
+bandwidth-bound kernel: it reads and writes every gamma row, 2 x N x ld x 8 bytes per iteration; timed as a
+step with an empty minibatch, i.e. prep + an idle pair kernel + the blend + the lambda kernel).
 `e2e` = the same iterations driven with HOST-chosen minibatches through svi_fa2_step (pair list uploaded
 every iteration) plus a held-out evaluation and a state download every `--report` iterations, which is what
 the reference-facing CLI does.  `cpu_baseline` = the oracle (oracle/oracle_fa2.c, 1 thread) on a bounded
@@ -128,19 +130,34 @@ def main():
         pairs += eng.info()["last_npairs"]
     value = pairs / (total_ms * 1e-3)
 
-    # ---- the blend alone (empty minibatch) ----
-    it_next = args.warmup + args.steps
+    # ---- eager mode (svi_fa2_config.eager_blend = 1): the reference's explicit O(N*K) pass every iteration ----
+    # timed on a second handle with the same draws; its blend kernel is the bandwidth-bound kernel of this path
+    eager = Fa2Engine(n, k, device=0, stream=stream.cuda_stream, eager_blend=1)
+    eager.set_state(gamma, lam)
+    eager.set_graph(links, heldout, shuffled)
+    eager.run(0, args.warmup, seed, count=False)
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    eager.run(args.warmup, args.steps, seed, count=False)
+    g1.record(stream)
+    torch.cuda.synchronize()
+    eager_ms = g0.elapsed_time(g1) / args.steps
+    it_e = args.warmup + args.steps
+    empty = np.zeros((0, 2), np.uint32)
     for _ in range(3):
-        eng.step(it_next, 0, 0, np.zeros((0, 2), np.uint32)); it_next += 1
+        eager.step(it_e, 0, 0, empty); it_e += 1
     torch.cuda.synchronize()
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nb = 20
     b0.record(stream)
     for _ in range(nb):
-        eng.step(it_next, 0, 0, np.zeros((0, 2), np.uint32)); it_next += 1
+        eager.step(it_e, 0, 0, empty); it_e += 1
     b1.record(stream)
     torch.cuda.synchronize()
     blend_ms = b0.elapsed_time(b1) / nb
+    eager.close()
+    it_next = args.warmup + args.steps
     info = eng.info()
     blend_bytes = 2 * n * info["ld"] * 8
     peak, peak_src = measured_peak_hbm()
@@ -187,13 +204,15 @@ def main():
                       "minibatches": "device Philox draws: %d link sets, %d non-informative sets of n/10" % tuple(types),
                       "pairs_in_timed_region": int(pairs), "rounds_per_pair_noninf": rounds_per_pair,
                       "l2": "gamma %.2f GB %s L2" % (n * info["ld"] * 8 / 1e9, "exceeds" if n * info["ld"] * 8 > 126e6 else "fits"),
-                      "tile": "G%d x V%d" % (info["lanes"], info["vec"]), "pair_blocks": info["pair_blocks"]},
-           "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * args.steps,
+                      "tile": "G%d x V%d" % (info["lanes"], info["vec"]), "pair_blocks": info["pair_blocks"],
+                      "decay": "lazy (scalar decay factor, no O(N*K) pass; svi_fa2_config.eager_blend = 0)",
+                      "eager_blend_ms_per_step": eager_ms},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": info["kernels_per_step"] * args.steps,
            "roofline": {"bound": "hbm", "kernel": "k_fa2_blend", "achieved": blend_bytes / (blend_ms * 1e-3) / 1e9,
                         "peak": peak, "unit": "GB/s", "frac": blend_bytes / (blend_ms * 1e-3) / 1e9 / peak,
                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(blend_bytes),
-                        "note": "timed as a whole empty-minibatch step (prep + idle pair kernel + blend + lambda): "
-                                "%.3f ms" % blend_ms},
+                        "note": "eager mode only (the default lazy mode never launches it); timed as a whole "
+                                "empty-minibatch step (prep + idle pair kernel + blend + lambda): %.3f ms" % blend_ms},
            "setup_s": {"generate": t_gen, "create+upload": t_create}, "wall_s_timed_region": t_wall}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(k, args.cpu_budget)

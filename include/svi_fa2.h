@@ -45,6 +45,13 @@ typedef struct svi_fa2_config {
   double   meanchangethresh;  /* env.meanchangethresh = 1e-5 (env.hh:337)                      */
   int32_t  nolambda;          /* env.nolambda                                                  */
   int32_t  device;            /* CUDA ordinal, -1 = current                                    */
+  /* How the decay of the rows a minibatch does NOT touch (src/fastamm2.cc:614-620) is applied.  Every
+   * node shares one step size (the reference bumps every _nodec[i] every iteration), so
+   * (gamma - alpha) of all untouched rows shrinks by the same factor (1 - rho):
+   *   0 (default): LAZY -- that factor is carried as one scalar c (rows store u, gamma = alpha + c*u);
+   *                no O(N*K) pass per iteration, the result differs from the eager one by rounding only;
+   *   1          : EAGER -- every row is read and written every iteration (k_fa2_blend), as the reference does. */
+  int32_t  eager_blend;
 } svi_fa2_config;
 
 /* Fill `cfg` with the reference's defaults for (n, k). */

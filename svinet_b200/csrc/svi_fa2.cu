@@ -100,6 +100,7 @@ struct svi_fa2 {
   Fa2Ops ops{};
   Fa2Params P{};
   uint64_t nodec = 0;          // host mirror of _nodec
+  double log_c = 0.0;          // host mirror of log(cscale) (lazy mode): decides when to re-base
   uint64_t device_bytes = 0;
   bool have_graph = false;
   // owned device memory
@@ -161,11 +162,23 @@ void launch_draw(svi_fa2 *h, uint32_t iter, uint64_t seed) {
   svi::k_fa2_draw_tail<<<1, 1024, 0, h->stream>>>(h->P, iter, lo, hi, h->draw_blocks);
 }
 
-void launch_iteration(svi_fa2 *h) {
+// prep, pairs, [blend], lambda; `nodec` = the node counter this iteration runs with
+void launch_iteration(svi_fa2 *h, uint64_t nodec) {
   h->ops.prep(h->P, h->stream);
   h->ops.pairs(h->P, h->stream);
-  h->ops.blend(h->P, h->stream);
+  if (!h->P.lazy) h->ops.blend(h->P, h->stream);
   svi::k_fa2_lambda<<<1, 256, 0, h->stream>>>(h->P, (uint32_t)h->ops.cap);
+  if (h->P.lazy) {
+    // c shrinks by (1 - rho) per iteration: exp(-2 sqrt(T)) in the long run.  Re-base the stored rows long
+    // before c*u leaves the FP64 range (every ~2e4 iterations at the default step sizes).
+    const double rho = std::pow(h->cfg.nodetau0 + (double)nodec, -1 * h->cfg.nodekappa);
+    h->log_c += std::log1p(-rho);
+    if (h->log_c < -230.0) {
+      svi::k_fa2_fold<<<h->sms * 8, 256, 0, h->stream>>>(h->P);
+      svi::k_fa2_reset_scale<<<1, 1, 0, h->stream>>>(h->P);
+      h->log_c = 0.0;
+    }
+  }
 }
 
 }  // namespace
@@ -180,7 +193,7 @@ void svi_fa2_default_config(svi_fa2_config *c, uint32_t n, uint32_t k) {
   c->eta0 = 1.0; c->eta1 = 1.0; c->epsilon = 1e-30;
   c->tau0 = 1025.0; c->kappa = 0.9; c->nodetau0 = 1025.0; c->nodekappa = 0.5;
   c->inf_epsilon = 0.5; c->m_sets = 10; c->online_iterations = 50; c->meanchangethresh = 1e-5;
-  c->nolambda = 0; c->device = -1;
+  c->nolambda = 0; c->device = -1; c->eager_blend = 0;
 }
 
 int svi_fa2_create(const svi_fa2_config *cfg, svi_fa2 **out) {
@@ -214,6 +227,7 @@ int svi_fa2_create(const svi_fa2_config *cfg, svi_fa2 **out) {
   P.tau0 = cfg->tau0; P.kappa = cfg->kappa; P.nodetau0 = cfg->nodetau0; P.nodekappa = cfg->nodekappa;
   P.inf_epsilon = cfg->inf_epsilon; P.online_iters = cfg->online_iterations; P.m_sets = cfg->m_sets;
   P.nolambda = cfg->nolambda ? 1u : 0u;
+  P.lazy = cfg->eager_blend ? 0u : 1u;
   P.pair_blocks = (uint32_t)ops.pair_blocks(h->sms);
   const uint32_t setsize = (uint32_t)((double)cfg->n / (double)cfg->m_sets);
   P.cap_pairs = std::max<uint32_t>(setsize, 1024);
@@ -275,17 +289,18 @@ int svi_fa2_set_state(svi_fa2 *h, const double *gamma, const double *lambda, uin
   DevGuard guard(h->device);
   const Fa2Params &P = h->P;
   const size_t nk = (size_t)P.n * P.k;
-  if (P.ld == P.k) {
-    SVI_CK(cudaMemcpyAsync(h->d_gamma, gamma, nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  } else {
+  {
     int rc = ensure_stage(h, nk * sizeof(double));
     if (rc) return rc;
     SVI_CK(cudaMemcpyAsync(h->d_stage, gamma, nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    svi::k_pad_rows<<<h->sms * 8, 256, 0, h->stream>>>(h->d_stage, h->d_gamma, P.n, P.k, P.ld);
+    // lazy: rows store u = gamma - alpha with c = 1
+    svi::k_fa2_import<<<h->sms * 8, 256, 0, h->stream>>>(h->d_stage, h->d_gamma, P.n, P.k, P.ld, P.lazy ? P.alpha : 0.0);
   }
   SVI_CK(cudaMemcpyAsync(h->d_lambda, lambda, 2 * (size_t)P.k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   memset(h->h_ctrl, 0, sizeof(Fa2Ctrl));
   h->h_ctrl->nodec = (double)nodec;
+  h->h_ctrl->cscale = 1.0;
+  h->log_c = 0.0;
   SVI_CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof(Fa2Ctrl), cudaMemcpyHostToDevice, h->stream));
   SVI_CK(cudaMemsetAsync(h->d_touched, 0, P.n, h->stream));
   h->nodec = nodec;
@@ -300,14 +315,10 @@ int svi_fa2_get_state(svi_fa2 *h, double *gamma, double *lambda) {
   const Fa2Params &P = h->P;
   const size_t nk = (size_t)P.n * P.k;
   if (gamma) {
-    if (P.ld == P.k) {
-      SVI_CK(cudaMemcpyAsync(gamma, h->d_gamma, nk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    } else {
-      int rc = ensure_stage(h, nk * sizeof(double));
-      if (rc) return rc;
-      svi::k_unpad_rows<<<h->sms * 8, 256, 0, h->stream>>>(h->d_gamma, h->d_stage, P.n, P.k, P.ld);
-      SVI_CK(cudaMemcpyAsync(gamma, h->d_stage, nk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    }
+    int rc = ensure_stage(h, nk * sizeof(double));
+    if (rc) return rc;
+    svi::k_fa2_export<<<h->sms * 8, 256, 0, h->stream>>>(P, h->d_stage);
+    SVI_CK(cudaMemcpyAsync(gamma, h->d_stage, nk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   }
   if (lambda)
     SVI_CK(cudaMemcpyAsync(lambda, h->d_lambda, 2 * (size_t)P.k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -351,7 +362,7 @@ int svi_fa2_step(svi_fa2 *h, uint32_t iter, uint32_t type, uint32_t start, uint6
   hc->scale = type == 0 ? (double)c.n / (2 * (1 - c.inf_epsilon))                       // :591-592
                         : ((double)c.n * (double)c.m_sets) / (2 * c.inf_epsilon);
   SVI_CK(cudaMemcpyAsync(h->d_ctrl, hc, offsetof(Fa2Ctrl, nodec), cudaMemcpyHostToDevice, h->stream));
-  launch_iteration(h);
+  launch_iteration(h, h->nodec);
   h->nodec++;
   SVI_CK(cudaGetLastError());
   return SVI_OK;
@@ -430,7 +441,7 @@ int svi_fa2_run(svi_fa2 *h, uint32_t iter0, uint32_t iters, uint64_t seed, uint6
   }
   for (uint32_t i = 0; i < iters; ++i) {
     launch_draw(h, iter0 + i, seed);
-    launch_iteration(h);
+    launch_iteration(h, h->nodec + i);
   }
   h->nodec += iters;
   SVI_CK(cudaGetLastError());
@@ -516,7 +527,7 @@ int svi_fa2_get_info(svi_fa2 *h, svi_fa2_info *info) {
   info->ld = h->P.ld; info->lanes = (uint32_t)h->ops.lanes; info->vec = (uint32_t)h->ops.vec;
   info->pair_blocks = h->P.pair_blocks; info->device_bytes = h->device_bytes;
   info->last_npairs = c.npairs; info->last_rounds = c.last_rounds;
-  info->kernels_per_step = h->have_graph ? 7 : 4;   // 3 draw launches + prep, pairs, blend, lambda
+  info->kernels_per_step = (h->have_graph ? 3 : 0) + (h->P.lazy ? 3 : 4);   // [3 draw launches] prep, pairs, [blend], lambda
   return SVI_OK;
 }
 

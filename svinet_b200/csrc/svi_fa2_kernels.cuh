@@ -16,7 +16,12 @@
 //                right there; start-node phi and phi1*phi2 go to per-group shared-memory accumulators
 //                and leave as per-block partial rows (fixed order: run-to-run deterministic)
 //   k_fa2_blend  every other row: decay towards alpha (the bandwidth-bound pass, 2 x N x K x 8 bytes);
-//                the start row gets the reduced partials
+//                the start row gets the reduced partials.  EAGER mode only.  In the default LAZY mode the
+//                decay (gamma - alpha) *= (1 - rho) of the untouched rows -- the same factor for every row,
+//                because the reference bumps every node's counter every iteration -- is carried as ONE scalar:
+//                rows store u with gamma = alpha + c*u, an iteration multiplies c by (1 - rho), touched rows
+//                get u += rho*scale*gammat / c, and the O(N*K) pass disappears (k_fa2_fold re-bases u <- c*u
+//                every few 1e4 iterations, before c can underflow)
 //   k_fa2_lambda one block: reduce the phi1*phi2 partials, blend lambda, advance the node counter
 //   k_fa2_draw_* the minibatch itself, from a Philox4x32-10 stream keyed by (seed, iter)
 #pragma once
@@ -29,6 +34,7 @@ struct Fa2Ctrl {            // one iteration's control block, device resident
   uint64_t sampled_inc;     // the reference's _total_pairs_sampled increment
   double rho_node, rho_t, scale;
   double nodec;             // _nodec[i] (identical for every node: each is bumped every iteration)
+  double cscale;            // lazy decay: gamma = alpha + cscale * stored (1 in eager mode)
   uint64_t total_sampled, total_rounds, last_rounds;
 };
 
@@ -37,7 +43,9 @@ struct Fa2Params {
   double alpha, eta0, eta1, logeps, thresh, epsilon;
   double tau0, kappa, nodetau0, nodekappa, inf_epsilon;
   uint32_t online_iters, m_sets, nolambda;
-  double *gamma;            // [n*ld]
+  uint32_t lazy;            // 1: rows hold u with gamma = alpha + cscale*u, the decay of untouched rows is the scalar
+                            //    update cscale *= (1 - rho) and no O(N*K) pass runs; 0: rows hold gamma, k_fa2_blend runs
+  double *gamma;            // [n*ld]  (lazy: u)
   double *lambda;           // [k*2]
   double *elogbeta;         // [2*ld]  column 0 then column 1
   double *elogf;            // [ld]    -inf beyond k
@@ -92,17 +100,32 @@ __device__ __forceinline__ void group_softmax(double2 (&t)[V], unsigned mask) {
   }
 }
 
+// stored row element -> gamma: eager (cs, a0) = (1, 0), exact; lazy (cs, a0) = (cscale, alpha)
+struct Fa2Map {
+  double cs, a0;
+  __device__ __forceinline__ double operator()(double u) const { return fma(cs, u, a0); }
+};
+__device__ __forceinline__ Fa2Map fa2_map(const Fa2Params &P, const Fa2Ctrl &c) {
+  Fa2Map m;
+  m.cs = P.lazy ? c.cscale : 1.0;
+  m.a0 = P.lazy ? P.alpha : 0.0;
+  return m;
+}
+
 // Elogpi row of node a from its gamma row (FastAMM2::set_dir_exp(a,..), src/fastamm2.hh:424-435);
 // pad columns -> -inf
 template <int G, int V>
-__device__ __forceinline__ void elogpi_row(const Fa2Params &P, uint32_t a, uint32_t lane, unsigned mask,
-                                           double2 (&e)[V]) {
+__device__ __forceinline__ void elogpi_row(const Fa2Params &P, const Fa2Map &gm, uint32_t a, uint32_t lane,
+                                           unsigned mask, double2 (&e)[V]) {
   const double *row = P.gamma + (size_t)a * P.ld;
   double s = 0.0;
 #pragma unroll
   for (int j = 0; j < V; ++j) {
-    e[j] = ld_row2(row, 2u * (lane + G * j), P.ld);
-    s += e[j].x + e[j].y;                       // pad columns hold 0
+    const uint32_t c = 2u * (lane + G * j);
+    e[j] = ld_row2(row, c, P.ld);
+    e[j].x = c < P.k ? gm(e[j].x) : 0.0;
+    e[j].y = c + 1u < P.k ? gm(e[j].y) : 0.0;
+    s += e[j].x + e[j].y;
   }
   s = group_sum<G>(s, mask);
   const double psi_sum = digamma_pos(s);
@@ -203,7 +226,7 @@ __global__ void __launch_bounds__(128) k_fa2_prep(const Fa2Params P) {
   if (threadIdx.x < G) {   // Elogpi of the start node, by the first group
     const unsigned mask = group_mask<G>();
     double2 e[V];
-    elogpi_row<G, V>(P, c.start, threadIdx.x, mask, e);
+    elogpi_row<G, V>(P, fa2_map(P, c), c.start, threadIdx.x, mask, e);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const uint32_t col = 2u * (threadIdx.x + G * j);
@@ -228,6 +251,9 @@ __global__ void __launch_bounds__(T) k_fa2_pairs(const Fa2Params P) {
   __syncthreads();
   double *myS = accS + grp * CAP, *myL = accL + grp * CAP;
 
+  const Fa2Map gm = fa2_map(P, c);
+  // lazy: u_a += rho*scale*phi_a / c', c' = (1 - rho) * c the scale AFTER this iteration
+  const double lazy_coef = c.rho_node * c.scale / ((1.0 - c.rho_node) * c.cscale);
   double2 ef[V], es[V];
   load_kvec<G, V>(P.elogf, lane, P.ld, ef, 0.0);
   load_kvec<G, V>(P.epi_start, lane, P.ld, es, -CUDART_INF);
@@ -238,7 +264,7 @@ __global__ void __launch_bounds__(T) k_fa2_pairs(const Fa2Params P) {
     const bool start_is_p = p == c.start;
     const uint32_t a = start_is_p ? q : p;
     double2 ea[V], phi1[V], phi2[V];
-    elogpi_row<G, V>(P, a, lane, mask, ea);
+    elogpi_row<G, V>(P, gm, a, lane, mask, ea);
     uint32_t r;
     if (start_is_p) r = fa2_pair_core<G, V>(P, mask, y, es, ea, ef, lane, phi1, phi2);
     else r = fa2_pair_core<G, V>(P, mask, y, ea, es, ef, lane, phi1, phi2);
@@ -252,8 +278,13 @@ __global__ void __launch_bounds__(T) k_fa2_pairs(const Fa2Params P) {
       const double2 ps = start_is_p ? phi1[j] : phi2[j];
       if (col < P.ld) {
         double2 g = *reinterpret_cast<const double2 *>(grow + col);
-        g.x = col < P.k ? (1.0 - c.rho_node) * g.x + c.rho_node * (P.alpha + c.scale * pa.x) : 0.0;
-        g.y = col + 1u < P.k ? (1.0 - c.rho_node) * g.y + c.rho_node * (P.alpha + c.scale * pa.y) : 0.0;
+        if (P.lazy) {
+          g.x = col < P.k ? fma(lazy_coef, pa.x, g.x) : 0.0;
+          g.y = col + 1u < P.k ? fma(lazy_coef, pa.y, g.y) : 0.0;
+        } else {
+          g.x = col < P.k ? (1.0 - c.rho_node) * g.x + c.rho_node * (P.alpha + c.scale * pa.x) : 0.0;
+          g.y = col + 1u < P.k ? (1.0 - c.rho_node) * g.y + c.rho_node * (P.alpha + c.scale * pa.y) : 0.0;
+        }
         *reinterpret_cast<double2 *>(grow + col) = g;
       }
       myS[col] += ps.x;
@@ -261,7 +292,7 @@ __global__ void __launch_bounds__(T) k_fa2_pairs(const Fa2Params P) {
       myL[col] += phi1[j].x * phi2[j].x;       // lambdat[k][t] += phi1*phi2 (src/fastamm2.cc:994-996)
       myL[col + 1] += phi1[j].y * phi2[j].y;
     }
-    if (lane == 0) P.touched[a] = 1;
+    if (lane == 0 && !P.lazy) P.touched[a] = 1;
   }
   __syncthreads();
   for (uint32_t col = threadIdx.x; col < (uint32_t)CAP; col += T) {
@@ -311,6 +342,15 @@ __global__ void __launch_bounds__(T) k_fa2_blend(const Fa2Params P) {
 // ---- lambda blend (src/fastamm2.cc:626-638) + counters ----------------------------------------------
 static __global__ void k_fa2_lambda(const Fa2Params P, uint32_t cap) {
   const Fa2Ctrl c = *P.ctrl;
+  if (P.lazy) {   // the start row: u += rho*scale*(sum of its phis) / c'   (eager mode: k_fa2_blend does it)
+    const double coef = c.rho_node * c.scale / ((1.0 - c.rho_node) * c.cscale);
+    double *urow = P.gamma + (size_t)c.start * P.ld;
+    for (uint32_t z = threadIdx.x; z < P.k; z += blockDim.x) {
+      double s = 0.0;
+      for (uint32_t b = 0; b < P.pair_blocks; ++b) s += P.partS[(size_t)b * cap + z];
+      urow[z] = fma(coef, s, urow[z]);
+    }
+  }
   if (!P.nolambda) {
     for (uint32_t z = threadIdx.x; z < P.k; z += blockDim.x) {
       double s = 0.0;
@@ -326,6 +366,7 @@ static __global__ void k_fa2_lambda(const Fa2Params P, uint32_t cap) {
   if (threadIdx.x == 0) {
     Fa2Ctrl *w = P.ctrl;
     w->nodec = c.nodec + 1.0;
+    if (P.lazy) w->cscale = (1.0 - c.rho_node) * c.cscale;
     w->total_sampled = c.total_sampled + c.sampled_inc;
     w->total_rounds = c.total_rounds + c.last_rounds;
   }
@@ -513,6 +554,7 @@ __global__ void __launch_bounds__(128) k_fa2_heldout(const Fa2Params P, uint64_t
   if (i >= npairs) return;
   const uint32_t p = pp[i], q = qq[i];
   const int y = yy[i];
+  const Fa2Map gm = fa2_map(P, *P.ctrl);
   double2 gp[V], gq[V];
   double sp = 0.0, sq = 0.0;
 #pragma unroll
@@ -520,6 +562,8 @@ __global__ void __launch_bounds__(128) k_fa2_heldout(const Fa2Params P, uint64_t
     const uint32_t c0 = 2u * (lane + G * j);
     gp[j] = ld_row2(P.gamma + (size_t)p * P.ld, c0, P.ld);
     gq[j] = ld_row2(P.gamma + (size_t)q * P.ld, c0, P.ld);
+    gp[j].x = c0 < P.k ? gm(gp[j].x) : 0.0; gp[j].y = c0 + 1u < P.k ? gm(gp[j].y) : 0.0;
+    gq[j].x = c0 < P.k ? gm(gq[j].x) : 0.0; gq[j].y = c0 + 1u < P.k ? gm(gq[j].y) : 0.0;
     sp += gp[j].x + gp[j].y;
     sq += gq[j].x + gq[j].y;
   }
@@ -557,8 +601,9 @@ __global__ void __launch_bounds__(32) k_fa2_one_pair(const Fa2Params P, uint32_t
   const unsigned mask = group_mask<G>();
   const uint32_t lane = threadIdx.x;
   double2 ep[V], eq[V], ef[V], phi1[V], phi2[V];
-  elogpi_row<G, V>(P, p, lane, mask, ep);
-  elogpi_row<G, V>(P, q, lane, mask, eq);
+  const Fa2Map gm = fa2_map(P, *P.ctrl);
+  elogpi_row<G, V>(P, gm, p, lane, mask, ep);
+  elogpi_row<G, V>(P, gm, q, lane, mask, eq);
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     const uint32_t c = 2u * (lane + G * j);
@@ -574,5 +619,27 @@ __global__ void __launch_bounds__(32) k_fa2_one_pair(const Fa2Params P, uint32_t
   }
   if (lane == 0) *rounds_out = r;
 }
+
+// ---- lazy-mode plumbing: dense caller layout <-> stored rows, and the re-basing pass ------------------------
+// import: dst[n*ld] = (src[n*k] - a0) (lazy: u = gamma - alpha with c = 1; eager a0 = 0), pad = 0
+static __global__ void k_fa2_import(const double *src, double *dst, uint32_t n, uint32_t k, uint32_t ld, double a0) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n * ld; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t c = i % ld;
+    dst[i] = c < k ? src[(i / ld) * k + c] - a0 : 0.0;
+  }
+}
+// export: dst[n*k] = gamma = alpha + c*u (lazy) or the stored value (eager)
+static __global__ void k_fa2_export(const Fa2Params P, double *dst) {
+  const Fa2Map gm = fa2_map(P, *P.ctrl);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)P.n * P.k; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = gm(P.gamma[(i / P.k) * P.ld + i % P.k]);
+}
+// fold: u <- c*u for every row (then the host resets c to 1): bounds the dynamic range of c*u
+static __global__ void k_fa2_fold(const Fa2Params P) {
+  const double cs = P.ctrl->cscale;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)P.n * P.ld; i += (size_t)gridDim.x * blockDim.x)
+    P.gamma[i] *= cs;
+}
+static __global__ void k_fa2_reset_scale(const Fa2Params P) { P.ctrl->cscale = 1.0; }
 
 }  // namespace svi

@@ -22,7 +22,7 @@ class Fa2Config(C.Structure):
                 ("eta1", C.c_double), ("epsilon", C.c_double), ("tau0", C.c_double), ("kappa", C.c_double),
                 ("nodetau0", C.c_double), ("nodekappa", C.c_double), ("inf_epsilon", C.c_double),
                 ("m_sets", C.c_uint32), ("online_iterations", C.c_uint32), ("meanchangethresh", C.c_double),
-                ("nolambda", C.c_int32), ("device", C.c_int32)]
+                ("nolambda", C.c_int32), ("device", C.c_int32), ("eager_blend", C.c_int32)]
 
 
 class Fa2Info(C.Structure):

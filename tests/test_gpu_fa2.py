@@ -53,13 +53,13 @@ def test_phi_pair_matches_oracle(k):
     eng.close()
 
 
-def lockstep(case, iters):
+def lockstep(case, iters, eager=0):
     ent = MANIFEST[case]
     opts = fa2_opts(ent["flags"])
     with Scratch() as d:
         g = orc.Graph.read(input_path(ent["input"], d), ent["n"])
         m = orc.Fa2Model(g, ent["k"], **opts)
-        eng = Fa2Engine(m.n, m.k)
+        eng = Fa2Engine(m.n, m.k, eager_blend=eager)
         eng.set_state(m.gamma, m.lambda_)
         worst_g = worst_l = 0.0
         types = [0, 0]
@@ -85,11 +85,34 @@ def lockstep(case, iters):
     return worst_g, worst_l
 
 
+@pytest.mark.parametrize("eager", [0, 1], ids=["lazy", "eager"])
 @pytest.mark.parametrize("case,iters", [("fa2_c1_m200", 201), ("fa2_c1_k6_seed9_m500", 300), ("fa2_lfr_k28_m300", 120),
                                         ("fa2_c2_m120", 40)])
-def test_lockstep_with_reference_minibatches(case, iters):
-    wg, wl = lockstep(case, iters)
+def test_lockstep_with_reference_minibatches(case, iters, eager):
+    """Both treatments of the untouched rows' decay (svi_fa2_config.eager_blend): the default scalar form and
+    the reference's explicit pass over all N rows."""
+    wg, wl = lockstep(case, iters, eager)
     assert wg <= TOL_OFFICIAL and wl <= TOL_OFFICIAL
+
+
+def test_lazy_decay_equals_eager_blend_over_a_rebase():
+    """25 000 device-drawn iterations: the scalar decay factor falls below e^-230 and the stored rows are
+    re-based (k_fa2_fold) at least once; the state must still equal the eager pass's."""
+    n, k = 120, 5
+    links, gamma, lam, heldout, shuffled = _synthetic(n, k, 6, seed=3)
+    seed = 99
+    out = []
+    for eager in (0, 1):
+        e = Fa2Engine(n, k, eager_blend=eager)
+        e.set_state(gamma, lam)
+        e.set_graph(links, heldout, shuffled)
+        e.run(0, 25000, seed, count=False)
+        out.append(e.get_state())
+        assert e.info()["kernels_per_step"] == (6 if eager == 0 else 7)
+        e.close()
+    (gl, ll), (ge, le) = out
+    assert np.all(np.isfinite(gl)) and np.all(gl > 0)
+    assert rel_err(gl, ge) <= 1e-9 and rel_err(ll, le) <= 1e-9
 
 
 def test_free_running_matches_reference_fixture():
