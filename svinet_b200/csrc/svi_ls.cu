@@ -258,6 +258,8 @@ struct svi_ls {
   double *d_part = nullptr, *d_kvec = nullptr, *d_kpart = nullptr, *d_lambda = nullptr, *d_eb = nullptr;
   double *d_scale = nullptr, *d_stage = nullptr;
   uint32_t *d_conv = nullptr, *d_active = nullptr, *d_abits = nullptr, *d_mbits = nullptr;
+  uint32_t *d_conv_snap = nullptr;   // `converged` as the s3 sweep must see it when the refresh ran first
+  bool conv_snap_valid = false;
   size_t stage_elems = 0;
 };
 
@@ -280,7 +282,7 @@ void free_all(svi_ls *h) {
   void *ptrs[] = {h->d_col, h->d_seg_node, h->d_seg_beg, h->d_seg_cnt, h->d_node_seg_off, h->d_seg3_node,
                   h->d_seg3_beg, h->d_seg3_cnt, h->d_tl, h->d_b, h->d_mphi, h->d_gamma, h->d_gacc, h->d_part,
                   h->d_kvec, h->d_kpart, h->d_lambda, h->d_eb, h->d_scale, h->d_stage, h->d_conv, h->d_active,
-                  h->d_abits, h->d_mbits};
+                  h->d_abits, h->d_mbits, h->d_conv_snap};
   for (void *p : ptrs)
     if (p) cudaFree(p);
 }
@@ -615,7 +617,8 @@ int svi_ls_phase_node(svi_ls *h) {
 int svi_ls_phase_s3(svi_ls *h) {
   if (!h) return fail(SVI_ERR_INVALID, "null handle");
   DeviceGuard guard(h->device);
-  const Params &P = h->P;
+  Params P = h->P;
+  if (h->conv_snap_valid) P.conv = h->d_conv_snap;   // the reference's s3 loop (:731-746) runs BEFORE prune (:761)
   uint32_t cap3 = 2 * h->ops.lanes * h->ops.vec;
   if (h->ops.s3_ring) {
     h->ops.s3_ring(P, h->stream, h->blocks_s3);
@@ -633,6 +636,27 @@ int svi_ls_phase_finish(svi_ls *h, int annealing) {
   DeviceGuard guard(h->device);
   h->ops.lambda(h->P, h->stream, annealing, 1);
   h->ops.refresh(h->P, h->stream, true);
+  CK(cudaGetLastError());
+  return SVI_OK;
+}
+
+int svi_ls_phase_refresh(svi_ls *h, int annealing) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  if (!h->d_conv_snap) CK(cudaMalloc((void **)&h->d_conv_snap, std::max<size_t>(h->P.n, 1) * sizeof(uint32_t)));
+  CK(cudaMemcpyAsync(h->d_conv_snap, h->d_conv, (size_t)h->P.n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+  h->conv_snap_valid = true;
+  svi::k_scale<<<1, 256, 0, h->stream>>>(h->P, annealing);
+  h->ops.refresh(h->P, h->stream, true);
+  CK(cudaGetLastError());
+  return SVI_OK;
+}
+
+int svi_ls_phase_lambda(svi_ls *h, int annealing) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  h->ops.lambda(h->P, h->stream, annealing, 1);
+  h->conv_snap_valid = false;
   CK(cudaGetLastError());
   return SVI_OK;
 }

@@ -448,6 +448,11 @@ __global__ void k_lambda(const Params P, int annealing, int update_lambda) {
   }
 }
 
+// annealing rescale ones/sum[k] (:541-542) on its own, for drivers that run the refresh before the s3 sweep
+static __global__ void k_scale(const Params P, int annealing) {
+  for (uint32_t c = threadIdx.x; c < P.k; c += blockDim.x) P.scale[c] = annealing ? P.ones_d / P.kvec[c] : 1.0;
+}
+
 // K5: gamma <- gammanext (with the deferred annealing rescale, :541-542), set_dir_exp(gamma)
 // (src/linksampling.hh:171-187), the sweep factor b = exp(Elogpi - rowmax), and prune /
 // check_and_set_converged (src/linksampling.cc:456-491).  One group per node row.

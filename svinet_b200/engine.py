@@ -40,7 +40,8 @@ ABI_SYMBOLS = [
     "svi_ls_create", "svi_ls_destroy", "svi_ls_set_stream", "svi_ls_sync", "svi_ls_set_state",
     "svi_ls_get_state", "svi_ls_set_converged", "svi_ls_get_converged", "svi_ls_step",
     "svi_ls_get_membership", "svi_ls_heldout", "svi_ls_get_kvectors", "svi_ls_phase_phi",
-    "svi_ls_phase_node", "svi_ls_phase_s3", "svi_ls_phase_finish", "svi_ls_device_buffer",
+    "svi_ls_phase_node", "svi_ls_phase_s3", "svi_ls_phase_finish", "svi_ls_phase_refresh", "svi_ls_phase_lambda",
+    "svi_ls_device_buffer",
     "svi_ls_get_info", "svi_ls_last_error", "svi_ls_abi_version",
 ]
 
@@ -72,6 +73,8 @@ def load_library(path=None):
     L.svi_ls_phase_node.argtypes = [vp]
     L.svi_ls_phase_s3.argtypes = [vp]
     L.svi_ls_phase_finish.argtypes = [vp, C.c_int]
+    L.svi_ls_phase_refresh.argtypes = [vp, C.c_int]
+    L.svi_ls_phase_lambda.argtypes = [vp, C.c_int]
     L.svi_ls_device_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.svi_ls_get_info.argtypes = [vp, C.POINTER(SviInfo)]
     L.svi_ls_last_error.restype = C.c_char_p
@@ -192,6 +195,12 @@ class LinkSamplingEngine:
 
     def phase_finish(self, annealing):
         _check(self.L, self.L.svi_ls_phase_finish(self.h, int(annealing)))
+
+    def phase_refresh(self, annealing):
+        _check(self.L, self.L.svi_ls_phase_refresh(self.h, int(annealing)))
+
+    def phase_lambda(self, annealing):
+        _check(self.L, self.L.svi_ls_phase_lambda(self.h, int(annealing)))
 
     def membership_bits(self):
         bits = np.empty((self.n, self.words), dtype=np.uint32)

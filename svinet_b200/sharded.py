@@ -9,11 +9,12 @@ has three real exchange steps, done with NCCL over NVLink/NVSwitch:
 
     phase_phi ; phase_node
         all-reduce   sum, s1, s2            (3 K-vectors; `sum` feeds the annealing rescale, :541-542)
-        all-gather   mphi rows              (N x K doubles in total)
-    phase_s3
-        all-reduce   s3                     (1 K-vector)
-    phase_finish
-        all-gather   exp(Elogpi) rows, converged[]   (+ active masks once iter > 1000)
+        all-gather   mphi rows              (N x K doubles in total)      | beside  phase_refresh
+    phase_s3                                                              | beside  all-gather exp(Elogpi) rows,
+        all-reduce   s3                     (1 K-vector)                  |         converged[] (+ active masks)
+    phase_lambda
+
+(`overlap=False` keeps the plain order phase_s3 ; phase_finish ; all-gathers.)
 
 The row all-gathers are the only bulk traffic: 2 x N*K*8 bytes per iteration (3.2 GB at n=1M, k=200)
 against ~480 GB of local HBM traffic divided by the number of GPUs.
@@ -86,8 +87,17 @@ class CudaShardEngine:
 
 
 class ShardedLinkSampling:
-    def __init__(self, n, k, links, rank, world, device=0, stream=None, engine_factory=None, group=None, **kw):
+    def __init__(self, n, k, links, rank, world, device=0, stream=None, engine_factory=None, group=None,
+                 overlap=True, **kw):
         self.n, self.k, self.rank, self.world, self.group = n, k, rank, world, group
+        # overlap=True: the iteration order of _step_overlapped; over NCCL the bulk row exchanges additionally get
+        # their own communicator and a side stream so that they run beside the kernels
+        self.overlap = overlap
+        self.side = self.bulk_group = None
+        if overlap and world > 1 and dist.get_backend(group) == "nccl":
+            ranks = dist.get_process_group_ranks(group) if group is not None else list(range(dist.get_world_size()))
+            self.bulk_group = dist.new_group(ranks=ranks, backend="nccl")
+            self.side = torch.cuda.Stream(device=device)
         links = np.ascontiguousarray(links, dtype=np.uint32).reshape(-1, 2)
         self.bounds = plan_shards(n, links, world)
         nb, ne = int(self.bounds[rank]), int(self.bounds[rank + 1])
@@ -106,7 +116,7 @@ class ShardedLinkSampling:
     def _allreduce(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
-    def _allgather_rows(self, name):
+    def _allgather_rows(self, name, bulk=False):
         """Every rank publishes its own row block of the (replicated-layout) buffer `name`, in place.
 
         The blocks are uneven (edge-balanced), so this is an all-gather-v.  Over NCCL it is ONE group of
@@ -114,6 +124,7 @@ class ShardedLinkSampling:
         NVLink ports work at once; a sequence of `world` broadcasts (the gloo path of the CPU tests)
         serialises them and measured 2x slower at 8 GPUs."""
         buf = self._buf[name]
+        group = self.bulk_group if (bulk and self.bulk_group is not None) else self.group
         blocks = [buf[int(self.bounds[r]):int(self.bounds[r + 1])] for r in range(self.world)]
         if dist.get_backend(self.group) == "nccl" and self.world > 1:
             mine = blocks[self.rank]
@@ -121,15 +132,15 @@ class ShardedLinkSampling:
             for d in range(1, self.world):
                 dst, src = (self.rank + d) % self.world, (self.rank - d) % self.world
                 if mine.shape[0]:
-                    ops.append(dist.P2POp(dist.isend, mine, self._global(dst), group=self.group))
+                    ops.append(dist.P2POp(dist.isend, mine, self._global(dst), group=group))
                 if blocks[src].shape[0]:
-                    ops.append(dist.P2POp(dist.irecv, blocks[src], self._global(src), group=self.group))
+                    ops.append(dist.P2POp(dist.irecv, blocks[src], self._global(src), group=group))
             for w in (dist.batch_isend_irecv(ops) if ops else []):
                 w.wait()
             return
         for r in range(self.world):
             if blocks[r].shape[0]:
-                dist.broadcast(blocks[r], src=self._global(r), group=self.group)
+                dist.broadcast(blocks[r], src=self._global(r), group=group)
 
     def _global(self, r):
         return dist.get_global_rank(self.group, r) if self.group is not None else r
@@ -138,6 +149,9 @@ class ShardedLinkSampling:
         self.eng.set_state(gamma, lam)     # derives the factors of ALL rows, no exchange needed
 
     def step(self, it, annealing, write_comm, events=None, stream=None):
+        if self.overlap:
+            return self._step_overlapped(it, annealing, write_comm, events, stream)
+
         def mark(i):
             if events is not None:
                 events[i].record(stream) if stream is not None else events[i].record()
@@ -157,6 +171,62 @@ class ShardedLinkSampling:
         if it >= 1000:                     # the active-set branch reads neighbours' masks (:634)
             self._allgather_rows("active")
             self._allgather_rows("active_bits")
+
+    def _step_overlapped(self, it, annealing, write_comm, events=None, stream=None):
+        """Same iteration with the refresh moved in front of the s3 sweep (svi_ls_phase_refresh /
+        svi_ls_phase_lambda), so that the bulk exchanges run beside compute on a side stream and their own
+        communicator: the mphi gather beside the refresh, the exp(Elogpi) / converged gather beside the s3
+        sweep.  Only the mphi gather stays exposed."""
+        def mark(i):
+            if events is not None:
+                events[i].record(stream) if stream is not None else events[i].record()
+        cuda = self.side is not None
+        main = torch.cuda.current_stream() if cuda else None
+        kv = self._buf["kvec"]
+
+        def on_side(after, fn):
+            """run fn() on the side stream once `after` (an event of the main stream) has happened"""
+            if not cuda:
+                fn()
+                return None
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(after)
+                fn()
+                done = torch.cuda.Event()
+                done.record(self.side)
+            return done
+
+        def event():
+            if not cuda:
+                return None
+            e = torch.cuda.Event()
+            e.record(main)
+            return e
+
+        self.eng.phase_phi(it, write_comm)
+        mark(1)
+        self.eng.phase_node()
+        self._allreduce(kv[0:3])
+        got_mphi = on_side(event(), lambda: self._allgather_rows("mphi", bulk=True))
+        self.eng.phase_refresh(annealing)
+
+        def publish():
+            self._allgather_rows("exppi", bulk=True)
+            self._allgather_rows("converged", bulk=True)
+            if it >= 1000:
+                self._allgather_rows("active", bulk=True)
+                self._allgather_rows("active_bits", bulk=True)
+        refreshed = event()
+        if cuda:
+            main.wait_event(got_mphi)
+        mark(2)
+        self.eng.phase_s3()
+        published = on_side(refreshed, publish)
+        self._allreduce(kv[3:4])
+        mark(3)
+        self.eng.phase_lambda(annealing)
+        if cuda:
+            main.wait_event(published)
 
     def gather_state(self):
         """Full gamma [n,k] and lambda [k,2] on every rank (for save_model / parity checks)."""

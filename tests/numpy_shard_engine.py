@@ -34,6 +34,7 @@ class NumpyShardEngine:
         self.abits = np.zeros((n, self.words), dtype=np.int32)
         self.mbits = np.zeros((n, self.words), dtype=np.int32)
         self.acc = z(n, k)
+        self.conv_snap = None
 
     def buffer(self, name):
         arr = {"exppi": self.b, "mphi": self.mphi, "gamma": self.gamma, "kvec": self.kvec, "converged": self.conv,
@@ -97,7 +98,8 @@ class NumpyShardEngine:
         s3 = np.zeros(self.k)
         o = self.own
         p, q = self.src[o], self.dst[o]
-        pc, qc = self.conv[p], self.conv[q]
+        conv = self.conv_snap if self.conv_snap is not None else self.conv
+        pc, qc = conv[p], conv[q]
         full = ~((pc != 0) != (qc != 0))
         s3 += (self.mphi[p[full]] * self.mphi[q[full]]).sum(0)
         a = (pc != 0) & (qc == 0)
@@ -109,11 +111,22 @@ class NumpyShardEngine:
         self.kvec[3] = s3
 
     def phase_finish(self, annealing):
+        self.phase_lambda(annealing)
+        self._refresh_own_rows(annealing)
+
+    def phase_lambda(self, annealing):
         s, s1, s2, s3 = self.kvec
         self.lam[:, 0] = self.eta0 + s
         self.lam[:, 1] = self.eta1 + (s1 * s1 - s2 - s3)
-        self.scale[:] = self.ones / s if annealing else 1.0
         self._refresh_lambda()
+        self.conv_snap = None
+
+    def phase_refresh(self, annealing):
+        self.conv_snap = self.conv.copy()
+        self._refresh_own_rows(annealing)
+
+    def _refresh_own_rows(self, annealing):
+        self.scale[:] = self.ones / self.kvec[0] if annealing else 1.0
         rows = np.arange(self.nb, self.ne)
         g = self.gacc[rows].copy()
         has = self.tl[rows] != 0

@@ -287,6 +287,36 @@ def test_run_to_run_determinism():
     st.free()
 
 
+def test_refresh_before_s3_is_the_same_iteration():
+    """svi_ls_phase_refresh / svi_ls_phase_lambda (the order sharded drivers use to hide their exchanges): the
+    refresh, prune included, runs BEFORE the s3 sweep, which must still see the pre-prune `converged` flags.
+    assort-75-4 is a run where nodes converge sweep after sweep, so a sweep that read the post-prune flags
+    would differ; the split order must be bit-identical to svi_ls_step."""
+    with Scratch() as d:
+        g = orc.Graph.read(input_path("assort-75-4.txt", d), 75)
+        m = orc.Model(g, 4, use_validation_stop=0)
+        st = m.state
+        outs, newly = [], 0
+        for split in (False, True):
+            eng = engine_from_state(st, g.ones)
+            prev = eng.get_converged()[0]
+            for it in range(28):
+                ann, wc = it < 14, 1
+                if split:
+                    eng.phase_phi(it, wc); eng.phase_node(); eng.phase_refresh(ann); eng.phase_s3(); eng.phase_lambda(ann)
+                else:
+                    eng.step(it, ann, wc)
+                cur = eng.get_converged()[0]
+                newly += int((cur != prev).sum())
+                prev = cur
+            outs.append(eng.get_state() + eng.get_converged() + (eng.kvectors()["s3"],))
+            eng.close()
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b)
+        assert newly > 0          # nodes did converge on the way, i.e. prune changed flags the s3 sweep reads
+        m.close(); g.close()
+
+
 def test_heldout_matches_literal_double_sum():
     st, links = synthetic_state(800, 50, 6000, seed=3)
     st.step(0, 1, 0)

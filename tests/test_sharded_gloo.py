@@ -19,13 +19,13 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, n, k, links, gamma0, sched, conv0, out):
+def _worker(rank, world, port, n, k, links, gamma0, sched, conv0, out, overlap=True):
     sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from numpy_shard_engine import NumpyShardEngine
     from svinet_b200.sharded import ShardedLinkSampling
-    sh = ShardedLinkSampling(n, k, links, rank=rank, world=world, engine_factory=NumpyShardEngine)
+    sh = ShardedLinkSampling(n, k, links, rank=rank, world=world, engine_factory=NumpyShardEngine, overlap=overlap)
     sh.set_state(gamma0, np.ones((k, 2)))
     sh.eng.conv[:] = conv0
     res = []
@@ -39,8 +39,8 @@ def _worker(rank, world, port, n, k, links, gamma0, sched, conv0, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_equals_oracle_over_gloo(world, tmp_path):
+@pytest.mark.parametrize("world,overlap", [(2, True), (3, True), (2, False)])
+def test_sharded_equals_oracle_over_gloo(world, overlap, tmp_path):
     sys.path.insert(0, HERE)
     import oracle_py as orc
     from svinet_b200 import synth
@@ -65,7 +65,7 @@ def test_sharded_equals_oracle_over_gloo(world, tmp_path):
     st.refresh_expectations()
 
     out = str(tmp_path / "res.pt")
-    mp.spawn(_worker, args=(world, _free_port(), n, k, links, gamma0, sched, conv0, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, k, links, gamma0, sched, conv0, out, overlap), nprocs=world, join=True)
     got = torch.load(out, weights_only=False)
     bounds = got["bounds"]
     assert bounds[0] == 0 and bounds[-1] == n and np.all(np.diff(bounds) > 0)
