@@ -38,7 +38,9 @@ struct Fa2Tile {
     svi::k_fa2_pairs<G, V, T><<<P.pair_blocks, T, kSmemPairs, st>>>(P);
   }
   static void blend(const Fa2Params &P, cudaStream_t st) {
-    const uint32_t blocks = (uint32_t)(((uint64_t)P.n * G + T - 1) / T);
+    // 4 rows in flight per group (k_fa2_blend): a grid that covers the rows once, capped at 32 blocks per SM
+    const uint64_t need = ((uint64_t)P.n * G + 4 * T - 1) / (4 * T);
+    const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(need, 148ull * 32));
     svi::k_fa2_blend<G, V, T><<<blocks, T, 0, st>>>(P);
   }
   static void heldout(const Fa2Params &P, cudaStream_t st, uint64_t np, const uint32_t *p, const uint32_t *q,

@@ -236,8 +236,11 @@ __global__ void __launch_bounds__(128) k_fa2_prep(const Fa2Params P) {
 }
 
 // ---- the pairs -------------------------------------------------------------------------------------
+#ifndef SVI_FA2_MINB
+#define SVI_FA2_MINB 1
+#endif
 template <int G, int V, int T>
-__global__ void __launch_bounds__(T) k_fa2_pairs(const Fa2Params P) {
+__global__ void __launch_bounds__(T, SVI_FA2_MINB) k_fa2_pairs(const Fa2Params P) {
   extern __shared__ double smem[];
   constexpr int CAP = 2 * G * V;
   constexpr int GPB = T / G;
@@ -263,11 +266,15 @@ __global__ void __launch_bounds__(T) k_fa2_pairs(const Fa2Params P) {
     const uint32_t p = P.pairs[2 * i], q = P.pairs[2 * i + 1];
     const bool start_is_p = p == c.start;
     const uint32_t a = start_is_p ? q : p;
-    double2 ea[V], phi1[V], phi2[V];
-    elogpi_row<G, V>(P, gm, a, lane, mask, ea);
-    uint32_t r;
-    if (start_is_p) r = fa2_pair_core<G, V>(P, mask, y, es, ea, ef, lane, phi1, phi2);
-    else r = fa2_pair_core<G, V>(P, mask, y, ea, es, ef, lane, phi1, phi2);
+    double2 ep[V], eq[V], phi1[V], phi2[V];
+    elogpi_row<G, V>(P, gm, a, lane, mask, ep);
+    // one call site (the fixed point is ~40 KB of SASS with its inlined exp's): order the two Elogpi rows here
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      eq[j] = start_is_p ? ep[j] : es[j];
+      ep[j] = start_is_p ? es[j] : ep[j];
+    }
+    const uint32_t r = fa2_pair_core<G, V>(P, mask, y, ep, eq, ef, lane, phi1, phi2);
     if (lane == 0) my_rounds += r;
     // far endpoint: gammat[a] = its phi, touched exactly once -> blend here (src/fastamm2.cc:609-613)
     double *grow = P.gamma + (size_t)a * P.ld;
@@ -308,34 +315,56 @@ __global__ void __launch_bounds__(T) k_fa2_pairs(const Fa2Params P) {
 template <int G, int V, int T>
 __global__ void __launch_bounds__(T) k_fa2_blend(const Fa2Params P) {
   constexpr int CAP = 2 * G * V;
+  constexpr int U = 4;                       // rows in flight per group: a row is only V 16-byte loads per lane
   const uint32_t lane = threadIdx.x & (G - 1);
-  const uint32_t i = (blockIdx.x * T + threadIdx.x) / G;
-  if (i >= P.n) return;
+  const uint32_t grp = (blockIdx.x * T + threadIdx.x) / G, ngroups = gridDim.x * T / G;
   const Fa2Ctrl c = *P.ctrl;
-  if (P.touched[i]) {
-    if (lane == 0) P.touched[i] = 0;
-    return;
-  }
-  double *grow = P.gamma + (size_t)i * P.ld;
-  const bool is_start = i == c.start;
+  for (uint32_t base = grp; base < P.n; base += ngroups * U) {
+    uint32_t row[U];
+    bool live[U];
+    double2 g[U][V];
 #pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const uint32_t col = 2u * (lane + G * j);
-    if (col >= P.ld) continue;
-    double2 t = make_double2(0.0, 0.0);
-    if (is_start) {
-      for (uint32_t b = 0; b < P.pair_blocks; ++b) {
-        const double2 v = *reinterpret_cast<const double2 *>(P.partS + (size_t)b * CAP + col);
-        t.x += v.x;
-        t.y += v.y;
+    for (int u = 0; u < U; ++u) {
+      row[u] = base + u * ngroups;
+      live[u] = row[u] < P.n && !P.touched[row[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const uint32_t col = 2u * (lane + G * j);
+        g[u][j] = live[u] && col < P.ld ? __ldcs(reinterpret_cast<const double2 *>(P.gamma + (size_t)row[u] * P.ld + col))
+                                        : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (row[u] >= P.n) continue;
+      if (!live[u]) {                        // blended by the pair kernel: just clear the flag
+        if (lane == 0) P.touched[row[u]] = 0;
+        continue;
+      }
+      const bool is_start = row[u] == c.start;
+      double *grow = P.gamma + (size_t)row[u] * P.ld;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const uint32_t col = 2u * (lane + G * j);
+        if (col >= P.ld) continue;
+        double2 t = make_double2(0.0, 0.0);
+        if (is_start) {
+          for (uint32_t b = 0; b < P.pair_blocks; ++b) {
+            const double2 v = *reinterpret_cast<const double2 *>(P.partS + (size_t)b * CAP + col);
+            t.x += v.x;
+            t.y += v.y;
+          }
+        }
+        const double tx = is_start ? P.alpha + c.scale * t.x : P.alpha;
+        const double ty = is_start ? P.alpha + c.scale * t.y : P.alpha;
+        double2 o;
+        o.x = col < P.k ? (1.0 - c.rho_node) * g[u][j].x + c.rho_node * tx : 0.0;
+        o.y = col + 1u < P.k ? (1.0 - c.rho_node) * g[u][j].y + c.rho_node * ty : 0.0;
+        __stcs(reinterpret_cast<double2 *>(grow + col), o);
       }
     }
-    double2 g = *reinterpret_cast<const double2 *>(grow + col);
-    const double tx = is_start ? P.alpha + c.scale * t.x : P.alpha;
-    const double ty = is_start ? P.alpha + c.scale * t.y : P.alpha;
-    g.x = col < P.k ? (1.0 - c.rho_node) * g.x + c.rho_node * tx : 0.0;
-    g.y = col + 1u < P.k ? (1.0 - c.rho_node) * g.y + c.rho_node * ty : 0.0;
-    *reinterpret_cast<double2 *>(grow + col) = g;
   }
 }
 
