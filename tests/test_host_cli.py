@@ -177,3 +177,27 @@ def test_ingest_sort_dedup_matches_oracle_on_messy_input(cli):
             assert links.shape[0] == g.ones
             assert np.array_equal(links, m.state.arr("links")) and np.array_equal(gamma, m.state.arr("gamma"))
             m.close(); g.close()
+
+
+def test_fa2_resume_from_saved_model(cli):
+    """-rnode -stratified -load <dir/> (FastAMM2::load_model, fastamm2.cc:1717-1803): the run starts from exactly
+    the %.5f text of a saved gamma.txt / lambda.txt."""
+    from test_oracle_fa2_golden import fa2_opts
+    ent = MANIFEST["fa2_c1_m200"]
+    with Scratch() as d:
+        inp = input_path(ent["input"], d)
+        if not os.path.exists(os.path.join(d, ent["input"])):
+            os.symlink(inp, os.path.join(d, ent["input"]))
+        saved = os.path.join(d, "saved")
+        os.makedirs(saved)
+        for f in ("gamma.txt", "lambda.txt"):
+            open(os.path.join(saved, f), "w").write(golden_text("fa2_c1_m200", f))
+        dump = os.path.join(d, "dump"); os.makedirs(dump)
+        subprocess.check_call([cli, "-file", ent["input"], "-n", "75", "-k", "4", "-rnode", "-stratified", "-load", "saved/",
+                               "-label", "resumed", "-dump-init", dump], cwd=d, stdout=subprocess.DEVNULL)
+        gam = np.fromfile(os.path.join(dump, "gamma.f64")).reshape(75, 4)
+        lam = np.fromfile(os.path.join(dump, "lambda.f64")).reshape(4, 2)
+        want_g = np.array([[float(x) for x in l.split("\t")[2:]] for l in golden_text("fa2_c1_m200", "gamma.txt").strip().split("\n")])
+        want_l = np.array([[float(x) for x in l.split("\t")[1:]] for l in golden_text("fa2_c1_m200", "lambda.txt").strip().split("\n")])
+        assert np.array_equal(gam, want_g) and np.array_equal(lam, want_l)
+        assert os.path.isdir(os.path.join(d, "n75-k4-resumed-Srnode"))
