@@ -162,7 +162,7 @@ FastAMM2::~FastAMM2() {
 
 bool FastAMM2::edge_ok(const Edge &e) const {
   if (e.first == e.second) return false;
-  return !std::binary_search(heldout_sorted_.begin(), heldout_sorted_.end(), e);
+  return held_keys_.find(((uint64_t)e.first << 32) | e.second) == held_keys_.end();
 }
 
 void FastAMM2::get_random_edge(bool link, Edge &e) {
@@ -191,7 +191,7 @@ void FastAMM2::set_heldout_sample(int s) {
     if (y && c1 < p) { c1++; keep = true; }
     if (keep) {
       heldout_pairs_.push_back(e);
-      heldout_sorted_.insert(std::upper_bound(heldout_sorted_.begin(), heldout_sorted_.end(), e), e);
+      held_keys_.insert(((uint64_t)e.first << 32) | e.second);
     }
   }
 }
@@ -199,6 +199,8 @@ void FastAMM2::set_heldout_sample(int s) {
 void FastAMM2::init_heldout() {
   const int s = (int)(env_.heldout_ratio * net_.ones());         // :304
   set_heldout_sample(s);
+  heldout_sorted_ = heldout_pairs_;                              // std::map<Edge,bool> iteration order
+  std::sort(heldout_sorted_.begin(), heldout_sorted_.end());
   env_.plog("heldout ratio", env_.heldout_ratio);
   env_.plog("heldout pairs (1s and 0s)", (uint64_t)heldout_sorted_.size());
   env_.plog("precision ratio", env_.precision_ratio);
@@ -229,6 +231,7 @@ void FastAMM2::load_heldout() {
   heldout_sorted_ = heldout_pairs_;
   std::sort(heldout_sorted_.begin(), heldout_sorted_.end());
   heldout_sorted_.erase(std::unique(heldout_sorted_.begin(), heldout_sorted_.end()), heldout_sorted_.end());
+  for (const Edge &e : heldout_sorted_) held_keys_.insert(((uint64_t)e.first << 32) | e.second);
   env_.plog("stratified random node: loaded heldout pairs:", cnt);
 }
 

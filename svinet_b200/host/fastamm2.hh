@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <ctime>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "env.hh"
@@ -61,6 +62,7 @@ class FastAMM2 {
   std::vector<double> gamma_, lambda_;
   std::vector<uint32_t> shuffled_;
   std::vector<Edge> heldout_pairs_, heldout_sorted_;
+  std::unordered_set<uint64_t> held_keys_;    // membership test of the held-out set (first << 32 | second)
   std::vector<uint32_t> hp_, hq_;
   std::vector<uint8_t> hy_;
   std::vector<double> hll_;

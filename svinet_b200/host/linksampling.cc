@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <sstream>
 #include <thread>
 
@@ -47,6 +48,17 @@ void write_rows(FILE *f, uint32_t rows, F line) {
     for (auto &s : out) fwrite(s.data(), 1, s.size(), f);
   }
 }
+
+// SVINET_TIMING=1: wall-clock laps on stderr (development aid, not in the reference)
+struct Lap {
+  bool on = getenv("SVINET_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void operator()(const char *what) {
+    const auto now = std::chrono::steady_clock::now();
+    if (on) fprintf(stderr, "[linksampling] %-30s %.3f s\n", what, std::chrono::duration<double>(now - t).count());
+    t = now;
+  }
+};
 
 inline void append_fmt(std::string &s, const char *fmt, double v) {
   char b[64];
@@ -88,6 +100,7 @@ LinkSampling::LinkSampling(Env &env, Network &network)
     env_.plog("eta", sa.str());
   }
   if (env_.seed) rng_.set((unsigned long)env_.seed);             // :74-75
+  Lap lap;
 
   FILE *vef = open_or_die(env_.file("/validation-edges.txt"), "w", "validation edges");
   FILE *tef = open_or_die(env_.file("/test-edges.txt"), "w", "test edges");
@@ -104,6 +117,7 @@ LinkSampling::LinkSampling(Env &env, Network &network)
   fprintf(vef, "\n");
   fclose(vef);
   if (env_.load_test) fprintf(stderr, "svinet: -load-test is accepted but the test set is not used in this build\n");
+  lap("held-out draw");
 
   gamma_.assign((size_t)n_ * k_, 0.0);
   lambda_.assign((size_t)k_ * 2, 0.0);
@@ -120,6 +134,7 @@ LinkSampling::LinkSampling(Env &env, Network &network)
     }
   }
 
+  lap("init gamma/lambda");
   tf_ = open_or_die(env_.file("/test.txt"), "w", "test");
   vf_ = open_or_die(env_.file("/validation.txt"), "w", "validation");
   env_.plog("network ones", net_.ones());
@@ -127,6 +142,7 @@ LinkSampling::LinkSampling(Env &env, Network &network)
   lf_ = open_or_die(env_.file("/logl.txt"), "w", "logl");
 
   assign_training_links();                                       // :566 (no RNG use, so it can run here)
+  lap("assign_training_links");
   if (env_.dump_only) return;
 
   svi_ls_config cfg;
@@ -137,6 +153,7 @@ LinkSampling::LinkSampling(Env &env, Network &network)
   cfg.node_begin = 0; cfg.node_end = n_;
   DEV(svi_ls_create(&cfg, links_.data(), training_links_.data(), &dev_));
   DEV(svi_ls_set_state(dev_, gamma_.data(), lambda_.data()));
+  lap("svi_ls_create + set_state");
 
   // held-out pairs in std::map<Edge,bool> order (lexicographic), the order validation_likelihood sums in
   validation_sorted_ = validation_pairs_;
@@ -160,7 +177,7 @@ LinkSampling::~LinkSampling() {
 
 bool LinkSampling::edge_ok(const Edge &e) const {
   if (e.first == e.second) return false;
-  return !std::binary_search(validation_sorted_.begin(), validation_sorted_.end(), e);
+  return held_keys_.find(((uint64_t)e.first << 32) | e.second) == held_keys_.end();
 }
 
 void LinkSampling::get_random_edge(bool link, Edge &e) {
@@ -189,7 +206,7 @@ void LinkSampling::set_validation_sample(int s) {
     if (y && c1 < p) { c1++; keep = true; }
     if (keep) {
       validation_pairs_.push_back(e);
-      validation_sorted_.insert(std::upper_bound(validation_sorted_.begin(), validation_sorted_.end(), e), e);
+      held_keys_.insert(((uint64_t)e.first << 32) | e.second);
     }
   }
 }
@@ -225,6 +242,7 @@ void LinkSampling::load_validation() {
   validation_sorted_ = validation_pairs_;
   std::sort(validation_sorted_.begin(), validation_sorted_.end());
   validation_sorted_.erase(std::unique(validation_sorted_.begin(), validation_sorted_.end()), validation_sorted_.end());
+  for (const Edge &e : validation_sorted_) held_keys_.insert(((uint64_t)e.first << 32) | e.second);
   env_.plog("link sampling: loaded validation heldout pairs:", cnt);
 }
 
@@ -393,30 +411,42 @@ void LinkSampling::write_groups() {
 }
 
 void LinkSampling::write_communities(const std::string &name) {
-  // one line per non-empty link community, ascending k: external ids ascending, each followed by ' '
+  // one line per non-empty link community, ascending k: external ids ascending, each followed by ' '.
+  // Runs every report (every iteration with the default reportfreq): nodes are visited in external-id order
+  // (a permutation computed once), so every community's list comes out sorted without a per-report sort.
   const uint32_t words = (k_ + 31) / 32;
   if (member_bits_.size() != (size_t)n_ * words) member_bits_.assign((size_t)n_ * words, 0);
   if (have_membership_) DEV(svi_ls_get_membership(dev_, member_bits_.data()));
-  std::vector<std::vector<uint32_t>> comm(k_);
-  for (uint32_t p = 0; p < n_; ++p)
-    for (uint32_t w = 0; w < words; ++w) {
-      uint32_t bits = member_bits_[(size_t)p * words + w];
+  if (by_id_.size() != n_) {
+    by_id_.resize(n_);
+    for (uint32_t p = 0; p < n_; ++p) by_id_[p] = p;
+    std::sort(by_id_.begin(), by_id_.end(), [&](uint32_t a, uint32_t b) { return net_.seq2id(a) < net_.seq2id(b); });
+    // "<id> " of every node, formatted once
+    id_text_.clear();
+    id_off_.assign((size_t)n_ + 1, 0);
+    char b[16];
+    for (uint32_t i = 0; i < n_; ++i) {
+      id_text_.append(b, (size_t)snprintf(b, sizeof b, "%d ", net_.seq2id(by_id_[i])));
+      id_off_[i + 1] = (uint32_t)id_text_.size();
+    }
+  }
+  std::vector<std::string> line(k_);
+  for (uint32_t i = 0; i < n_; ++i) {
+    const uint32_t *w = &member_bits_[(size_t)by_id_[i] * words];
+    for (uint32_t wi = 0; wi < words; ++wi) {
+      uint32_t bits = w[wi];
       while (bits) {
-        const uint32_t c = w * 32 + (uint32_t)__builtin_ctz(bits);
+        const uint32_t c = wi * 32 + (uint32_t)__builtin_ctz(bits);
         bits &= bits - 1;
-        if (c < k_) comm[c].push_back(net_.seq2id(p));
+        if (c < k_) line[c].append(id_text_, id_off_[i], id_off_[i + 1] - id_off_[i]);
       }
     }
+  }
   FILE *f = open_or_die(env_.file(name), "w", "communities");
-  std::string line;
   for (uint32_t c = 0; c < k_; ++c) {
-    if (comm[c].empty()) continue;
-    std::sort(comm[c].begin(), comm[c].end());
-    line.clear();
-    char b[16];
-    for (uint32_t id : comm[c]) line.append(b, (size_t)snprintf(b, sizeof b, "%d ", id));
-    line.push_back('\n');
-    fwrite(line.data(), 1, line.size(), f);
+    if (line[c].empty()) continue;
+    line[c].push_back('\n');
+    fwrite(line[c].data(), 1, line[c].size(), f);
   }
   fclose(f);
 }
@@ -436,18 +466,30 @@ void LinkSampling::do_on_stop() {
 void LinkSampling::infer() {
   bool write_comm = false;
   const uint32_t rf = (uint32_t)env_.reportfreq;
+  Lap lap;
+  double t_step = 0, t_report = 0;
+  auto since = [](std::chrono::steady_clock::time_point a) {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
+  };
   while (1) {
     if (env_.max_iterations && iter_ > env_.max_iterations) {
       printf("+ Quitting: reached max iterations.\n");
       env_.plog("maxiterations reached", true);
       env_.terminate = true;
+      if (lap.on)
+        fprintf(stderr, "[linksampling] %u iterations: device steps %.3f s, reports (held-out + communities.txt) %.3f s\n",
+                iter_, t_step, t_report);
+      lap("iterations");
       do_on_stop();
+      lap("do_on_stop (writers)");
       exit(0);
     }
     if (env_.max_iterations == 1) write_comm = true;
     printf("\riteration %d: processing %zu links", iter_, links_.size() / 2);
     fflush(stdout);
+    auto t0 = std::chrono::steady_clock::now();
     DEV(svi_ls_step(dev_, iter_, annealing_ ? 1 : 0, write_comm ? 1 : 0));
+    if (lap.on) { DEV(svi_ls_sync(dev_)); t_step += since(t0); }
     if (write_comm) have_membership_ = true;
 
     if (env_.terminate) {             // SIGTERM: dump the model and carry on (:763-766)
@@ -456,12 +498,14 @@ void LinkSampling::infer() {
     }
     write_comm = (iter_ % rf == rf - 1);
     if (iter_ % rf == 0) {
+      t0 = std::chrono::steady_clock::now();
       if (validation_likelihood()) {
         do_on_stop();
         exit(0);
       }
       test_likelihood_line();
       log_communities();
+      t_report += since(t0);
     }
     iter_++;
   }

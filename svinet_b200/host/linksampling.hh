@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <ctime>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "env.hh"
@@ -60,9 +61,13 @@ class LinkSampling {
   std::vector<double> gamma_, lambda_;    // host mirrors (n*k, k*2)
   std::vector<Edge> validation_pairs_;    // draw order
   std::vector<Edge> validation_sorted_;   // std::map<Edge,bool> iteration order
+  std::unordered_set<uint64_t> held_keys_; // membership test of the held-out set (first << 32 | second)
   std::vector<uint32_t> links_;           // training links (p<q), reference order
   std::vector<double> training_links_;    // tl[p] = 2 x training degree
   std::vector<uint32_t> member_bits_;     // last write_comm tally fetched from the device
+  std::vector<uint32_t> by_id_;           // nodes in ascending external-id order (communities.txt order)
+  std::string id_text_;                   // their "<id> " strings, back to back
+  std::vector<uint32_t> id_off_;
   bool have_membership_ = false;
   bool annealing_ = true;
   double max_t_ = -2147483647, max_h_ = -2147483647, prev_h_ = -2147483647;
