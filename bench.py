@@ -378,6 +378,36 @@ def cpu_baseline_port(k, budget_s=20.0):
             "host_cpus": os.cpu_count()}
 
 
+def cpu_baseline_fa2_port(k, budget_s=15.0):
+    """cpu_baseline leg of bench_fa2.py (the -rnode -stratified path): oracle/oracle_fa2.c, 1 thread, bounded sample."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import oracle_py as orc
+    from svinet_b200 import synth
+    # one non-informative iteration costs ~ (n/10) pairs x rounds x 2K x 3 transcendentals (~20 ns each)
+    per_pair = 50 * 2 * k * 3 * 20e-9
+    n_s = int(max(400, min(40000, 10 * budget_s / (6 * per_pair))))
+    links = synth.mmsb_links(n_s, k, n_s * 20, seed=4321, device="cpu")
+    used = np.unique(links)
+    remap = np.zeros(n_s, dtype=np.int64); remap[used] = np.arange(used.size)
+    g = orc.Graph.from_pairs(remap[links.astype(np.int64)].astype(np.uint32), used.size)
+    m = orc.Fa2Model(g, k, max_iterations=0, reportfreq=1 << 30)
+    m.run(2)
+    pairs = iters = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget_s and iters < 64:
+        before = m.total_pairs_sampled
+        m.run(1)
+        pairs += m.total_pairs_sampled - before
+        iters += 1
+    dt = time.perf_counter() - t0
+    out = {"value": pairs / dt, "unit": "pair-updates/s", "cores": 1, "kind": "port", "iterations_per_s": iters / dt,
+           "sample": "oracle/oracle_fa2.c, %d iterations (reference mt19937 minibatches) on a synthetic MMSB sample "
+                     "n=%d k=%d links=%d" % (iters, g.n, k, g.ones), "host_cpus": os.cpu_count()}
+    m.close(); g.close()
+    return out
+
+
+
 def run_reference(args):
     """The reference's own CPU implementation on this box's host cores, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -444,7 +474,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the --impl reference arm")
-    args = ap.parse_args()
+    ap.add_argument("--path", default="ls", choices=["ls", "fa2"],
+                    help="ls = -link-sampling (the BASELINE.json metric); fa2 = -rnode -stratified, forwarded to bench_fa2.py")
+    args, rest = ap.parse_known_args()
+    if args.path == "fa2":
+        import bench_fa2
+        sys.argv = [sys.argv[0]] + rest + (["--workload", args.workload] if "--workload" in sys.argv else []) + \
+                   (["--steps", str(args.steps)] if "--steps" in sys.argv else []) + \
+                   (["--warmup", str(args.warmup)] if "--warmup" in sys.argv else []) + \
+                   (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+        return bench_fa2.main()
+    if rest:
+        ap.error("unrecognized arguments: %s" % " ".join(rest))
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         run_reference(args)

@@ -15,7 +15,8 @@ step with an empty minibatch, i.e. prep + an idle pair kernel + the blend + the 
 `e2e` = the same iterations driven with HOST-chosen minibatches through svi_fa2_step (pair list uploaded
 every iteration) plus a held-out evaluation and a state download every `--report` iterations, which is what
 the reference-facing CLI does.  `cpu_baseline` = the oracle (oracle/oracle_fa2.c, 1 thread) on a bounded
-sample of the workload.
+sample of the workload, through bench.py's cpu_baseline leg (this file never touches oracle/ itself).
+`python bench.py --path fa2 ...` forwards here.
 """
 import argparse
 import json
@@ -27,7 +28,7 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
-from bench import WORKLOADS, ClockSampler, fast_state, measured_peak_hbm   # noqa: E402
+from bench import WORKLOADS, ClockSampler, cpu_baseline_fa2_port, fast_state, measured_peak_hbm   # noqa: E402
 
 METRIC = "fa2_pair_updates_per_sec"
 UNIT = "pair-updates/s"
@@ -49,34 +50,6 @@ def make_problem(n, k, target, device):
     gamma = gamma / np.maximum(gamma.sum(axis=1, keepdims=True), 1e-300) * k * 1.0 + 0.01   # ~Gamma(100,.01)-scale rows
     lam = 1.0 + rng.gamma(100.0, 0.01, size=(k, 2))
     return links, heldout, hy, shuffled, gamma, lam
-
-
-def cpu_baseline(k, budget_s):
-    sys.path.insert(0, os.path.join(REPO, "tests"))
-    import oracle_py as orc
-    from svinet_b200 import synth
-    # one non-informative iteration costs ~ (n/10) pairs x rounds x 2K x 3 transcendentals (~20 ns each)
-    per_pair = 50 * 2 * k * 3 * 20e-9
-    n_s = int(max(400, min(40000, 10 * budget_s / (6 * per_pair))))
-    links = synth.mmsb_links(n_s, k, n_s * 20, seed=4321, device="cpu")
-    used = np.unique(links)
-    remap = np.zeros(n_s, dtype=np.int64); remap[used] = np.arange(used.size)
-    g = orc.Graph.from_pairs(remap[links.astype(np.int64)].astype(np.uint32), used.size)
-    m = orc.Fa2Model(g, k, max_iterations=0, reportfreq=1 << 30)
-    m.run(2)
-    pairs = iters = 0
-    t0 = time.perf_counter()
-    while time.perf_counter() - t0 < budget_s and iters < 64:
-        before = m.total_pairs_sampled
-        m.run(1)
-        pairs += m.total_pairs_sampled - before
-        iters += 1
-    dt = time.perf_counter() - t0
-    out = {"value": pairs / dt, "unit": UNIT, "cores": 1, "kind": "port", "iterations_per_s": iters / dt,
-           "sample": "oracle/oracle_fa2.c, %d iterations (reference mt19937 minibatches) on a synthetic MMSB sample "
-                     "n=%d k=%d links=%d" % (iters, g.n, k, g.ones), "host_cpus": os.cpu_count()}
-    m.close(); g.close()
-    return out
 
 
 def main():
@@ -215,7 +188,7 @@ def main():
                                 "empty-minibatch step (prep + idle pair kernel + blend + lambda): %.3f ms" % blend_ms},
            "setup_s": {"generate": t_gen, "create+upload": t_create}, "wall_s_timed_region": t_wall}
     if not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(k, args.cpu_budget)
+        out["cpu_baseline"] = cpu_baseline_fa2_port(k, args.cpu_budget)      # the oracle leg lives in bench.py
     print(json.dumps(out))
     eng.close()
 
