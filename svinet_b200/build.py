@@ -52,7 +52,7 @@ def build_cli(force=False, verbose=False):
     deps = srcs + hdrs + [os.path.join(REPO, "include", "svi_ls.h"), LIB]
     if not force and not _newer(CLI, deps):
         return CLI
-    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-g", "-Wall", "-I", os.path.join(REPO, "include"),
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O3", "-g", "-Wall", "-I", os.path.join(REPO, "include"),
            "-o", CLI] + srcs + ["-L", LIBDIR, "-lsvi_ls", "-Wl,-rpath,$ORIGIN", "-lpthread"]
     if verbose:
         print(" ".join(cmd))

@@ -247,18 +247,65 @@ void LinkSampling::load_validation() {
 }
 
 void LinkSampling::init_gamma2() {
-  std::vector<double> phi(k_);
+  // Reference (:374-401): for every link in (p, adjacency) order draw K uniforms, normalise, add the vector to
+  // both endpoints' rows -- one serial loop, 2*K*8 bytes of read-modify-write per link on random rows (122 s at
+  // 1e8 links, K = 200).  Same values, same order of additions per row, spread over the host threads:
+  //   producer  : the mt19937 stream for a chunk of links (inherently serial, but only the generator)
+  //   phase A   : per link, the reference's sum (index order) and division          -- parallel over links
+  //   phase B   : per NODE RANGE, walk the chunk's links in order and add into the rows of that range
+  //               (a row only ever sees its additions in link order)                 -- parallel over ranges
+  const uint32_t k = k_;
+  std::vector<uint32_t> lp, lq;
   for (uint32_t p = 0; p < n_; ++p)
-    for (uint32_t q : net_.get_edges(p)) {
-      if (p >= q) continue;
-      for (uint32_t c = 0; c < k_; ++c) phi[c] = rng_.uniform();
-      double s = .0;
-      for (uint32_t c = 0; c < k_; ++c) s += phi[c];
-      for (uint32_t c = 0; c < k_; ++c) phi[c] = phi[c] / s;
-      double *gp = &gamma_[(size_t)p * k_], *gq = &gamma_[(size_t)q * k_];
-      for (uint32_t c = 0; c < k_; ++c) gp[c] += phi[c];
-      for (uint32_t c = 0; c < k_; ++c) gq[c] += phi[c];
-    }
+    for (uint32_t q : net_.get_edges(p))
+      if (p < q) { lp.push_back(p); lq.push_back(q); }
+  const size_t nl = lp.size();
+  const size_t chunk = std::max<size_t>(256, std::min<size_t>(1u << 14, (size_t)(1u << 22) / std::max(1u, k)));
+  const unsigned nt = std::max(1u, std::min(16u, std::min<unsigned>(std::thread::hardware_concurrency(),
+                                                                    (unsigned)(nl / 4096 + 1))));
+  std::vector<double> buf[2] = {std::vector<double>(chunk * k), std::vector<double>(chunk * k)};
+  auto work = [&](const double *u0, size_t l0, size_t cnt) {
+    double *u = const_cast<double *>(u0);
+    std::vector<std::thread> th;
+    // phase A
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t] {
+        for (size_t i = cnt * t / nt; i < cnt * (t + 1) / nt; ++i) {
+          double *phi = u + i * k;
+          double s = .0;
+          for (uint32_t c = 0; c < k; ++c) s += phi[c];
+          for (uint32_t c = 0; c < k; ++c) phi[c] = phi[c] / s;
+        }
+      });
+    for (auto &x : th) x.join();
+    th.clear();
+    // phase B
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t] {
+        const uint32_t v0 = (uint32_t)((uint64_t)n_ * t / nt), v1 = (uint32_t)((uint64_t)n_ * (t + 1) / nt);
+        for (size_t i = 0; i < cnt; ++i) {
+          const uint32_t p = lp[l0 + i], q = lq[l0 + i];
+          const double *phi = u + i * k;
+          if (p >= v0 && p < v1) { double *g = &gamma_[(size_t)p * k]; for (uint32_t c = 0; c < k; ++c) g[c] += phi[c]; }
+          if (q >= v0 && q < v1) { double *g = &gamma_[(size_t)q * k]; for (uint32_t c = 0; c < k; ++c) g[c] += phi[c]; }
+        }
+      });
+    for (auto &x : th) x.join();
+  };
+  // double-buffered: the generator fills chunk i+1 while the workers consume chunk i
+  size_t l0 = 0;
+  int cur = 0;
+  size_t cnt = std::min(chunk, nl);
+  rng_.uniform_fill(buf[cur].data(), cnt * k);
+  while (l0 < nl) {
+    const size_t next_l0 = l0 + cnt, next_cnt = std::min(chunk, nl - next_l0);
+    std::thread producer([&] { if (next_cnt) rng_.uniform_fill(buf[cur ^ 1].data(), next_cnt * k); });
+    work(buf[cur].data(), l0, cnt);
+    producer.join();
+    l0 = next_l0;
+    cnt = next_cnt;
+    cur ^= 1;
+  }
 }
 
 int LinkSampling::load_model() {
@@ -306,21 +353,36 @@ int LinkSampling::load_model() {
 }
 
 void LinkSampling::assign_training_links() {
+  // :493-523.  tl[v] counts v's non-held-out adjacency entries TWICE (the reference bumps both endpoints for
+  // every adjacency direction); links_ lists the kept (p<q) pairs in (p, adjacency) order.  Node
+  // ranges are independent, so they run on the host threads and their link lists are concatenated in order.
   training_links_.assign(n_, 0.0);
   links_.clear();
-  for (uint32_t p = 0; p < n_; ++p)
-    for (uint32_t q : net_.get_edges(p)) {
-      if (!env_.accuracy) {
-        Edge e(p, q);
-        Network::order_edge(e);
-        if (!edge_ok(e)) continue;   // held out
+  const unsigned nt = std::max(1u, std::min(16u, std::min<unsigned>(std::thread::hardware_concurrency(), n_ / 4096 + 1)));
+  std::vector<std::vector<uint32_t>> part(nt);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t)
+    th.emplace_back([&, t] {
+      const uint32_t v0 = (uint32_t)((uint64_t)n_ * t / nt), v1 = (uint32_t)((uint64_t)n_ * (t + 1) / nt);
+      for (uint32_t p = v0; p < v1; ++p) {
+        uint32_t kept = 0;
+        for (uint32_t q : net_.get_edges(p)) {
+          if (!env_.accuracy) {
+            Edge e(p, q);
+            Network::order_edge(e);
+            if (!edge_ok(e)) continue;   // held out
+          }
+          ++kept;
+          if (p < q) { part[t].push_back(p); part[t].push_back(q); }
+        }
+        training_links_[p] = 2.0 * kept;
       }
-      training_links_[p]++;          // both adjacency directions count: tl = 2 x degree
-      training_links_[q]++;
-      if (p >= q) continue;
-      links_.push_back(p);
-      links_.push_back(q);
-    }
+    });
+  for (auto &x : th) x.join();
+  size_t total = 0;
+  for (auto &v : part) total += v.size();
+  links_.reserve(total);
+  for (auto &v : part) links_.insert(links_.end(), v.begin(), v.end());
 }
 
 bool LinkSampling::validation_likelihood() {
@@ -430,23 +492,37 @@ void LinkSampling::write_communities(const std::string &name) {
       id_off_[i + 1] = (uint32_t)id_text_.size();
     }
   }
-  std::vector<std::string> line(k_);
-  for (uint32_t i = 0; i < n_; ++i) {
-    const uint32_t *w = &member_bits_[(size_t)by_id_[i] * words];
-    for (uint32_t wi = 0; wi < words; ++wi) {
-      uint32_t bits = w[wi];
-      while (bits) {
-        const uint32_t c = wi * 32 + (uint32_t)__builtin_ctz(bits);
-        bits &= bits - 1;
-        if (c < k_) line[c].append(id_text_, id_off_[i], id_off_[i + 1] - id_off_[i]);
-      }
-    }
+  // every thread scans a slice of the id-ordered nodes into its own per-community buffers; a community's line is
+  // the concatenation of the slices in order, so the ids stay ascending
+  const unsigned nt = std::max(1u, std::min(16u, std::min(std::thread::hardware_concurrency(), n_ / 4096 + 1)));
+  std::vector<std::vector<std::string>> part(nt, std::vector<std::string>(k_));
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t] {
+        const uint32_t i0 = (uint32_t)((uint64_t)n_ * t / nt), i1 = (uint32_t)((uint64_t)n_ * (t + 1) / nt);
+        std::vector<std::string> &line = part[t];
+        for (uint32_t i = i0; i < i1; ++i) {
+          const uint32_t *w = &member_bits_[(size_t)by_id_[i] * words];
+          for (uint32_t wi = 0; wi < words; ++wi) {
+            uint32_t bits = w[wi];
+            while (bits) {
+              const uint32_t c = wi * 32 + (uint32_t)__builtin_ctz(bits);
+              bits &= bits - 1;
+              if (c < k_) line[c].append(id_text_, id_off_[i], id_off_[i + 1] - id_off_[i]);
+            }
+          }
+        }
+      });
+    for (auto &x : th) x.join();
   }
   FILE *f = open_or_die(env_.file(name), "w", "communities");
   for (uint32_t c = 0; c < k_; ++c) {
-    if (line[c].empty()) continue;
-    line[c].push_back('\n');
-    fwrite(line[c].data(), 1, line[c].size(), f);
+    size_t len = 0;
+    for (unsigned t = 0; t < nt; ++t) len += part[t][c].size();
+    if (!len) continue;
+    for (unsigned t = 0; t < nt; ++t) fwrite(part[t][c].data(), 1, part[t][c].size(), f);
+    fputc('\n', f);
   }
   fclose(f);
 }

@@ -7,6 +7,7 @@
 // polar normal (upstream GSL's exact variate stream is not reproducible here: GSL is not vendored).
 #ifndef SVINET_B200_RNG_HH
 #define SVINET_B200_RNG_HH
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -30,6 +31,28 @@ class Mt19937 {
     return y;
   }
   double uniform() { return next() / 4294967296.0; }
+  // `count` consecutive uniform() values; same stream, tempered a block at a time (vectorisable)
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+  __attribute__((target_clones("avx2", "default")))   // runtime dispatch: the build host is not the run host
+#endif
+  void uniform_fill(double *out, size_t count) {
+    size_t i = 0;
+    while (i < count) {
+      if (at_ >= N) refill();
+      const size_t take = std::min<size_t>(count - i, (size_t)(N - at_));
+      const uint32_t *src = x_ + at_;
+      for (size_t j = 0; j < take; ++j) {
+        uint32_t y = src[j];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680U;
+        y ^= (y << 15) & 0xefc60000U;
+        y ^= y >> 18;
+        out[i + j] = y / 4294967296.0;
+      }
+      at_ += (int)take;
+      i += take;
+    }
+  }
   unsigned long uniform_int(unsigned long n) {
     const unsigned long scale = 0xffffffffUL / n;
     unsigned long k;
@@ -78,11 +101,15 @@ class Mt19937 {
 
  private:
   static const int N = 624, M = 397;
-  void refill() {
-    for (int i = 0; i < N; ++i) {
-      const uint32_t y = (x_[i] & 0x80000000U) | (x_[(i + 1) % N] & 0x7fffffffU);
-      x_[i] = x_[(i + M) % N] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
-    }
+  void refill() {   // three modulo-free runs of the recurrence x[i] = x[i+M] ^ twist(x[i], x[i+1])
+    auto tw = [](uint32_t a, uint32_t b) {
+      const uint32_t y = (a & 0x80000000U) | (b & 0x7fffffffU);
+      return (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
+    };
+    int i = 0;
+    for (; i < N - M; ++i) x_[i] = x_[i + M] ^ tw(x_[i], x_[i + 1]);
+    for (; i < N - 1; ++i) x_[i] = x_[i + M - N] ^ tw(x_[i], x_[i + 1]);
+    x_[N - 1] = x_[M - 1] ^ tw(x_[N - 1], x_[0]);
     at_ = 0;
   }
   uint32_t x_[N];
