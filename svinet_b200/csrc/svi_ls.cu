@@ -58,7 +58,8 @@ struct Ops {
   void (*phi_ring)(const Params &, cudaStream_t, bool sparse, bool comm) = nullptr;
   void (*s3_ring)(const Params &, cudaStream_t, uint32_t blocks) = nullptr;
   int (*max_blocks_s3_ring)(int sms, uint32_t ld) = nullptr;
-  int ring_lanes = 0, ring_vec = 0, ring_depth = 0, ring_threads = 256;
+  int ring_lanes = 0, ring_vec = 0, ring_depth = 0, ring_threads = 256;   // tiling of phi_ring
+  int s3_lanes = 0, s3_vec = 0, s3_threads = 256;                         // tiling of s3_ring (may differ)
 };
 
 constexpr int kThreads = 256;
@@ -151,14 +152,23 @@ struct RingTile {
       per_sm = 1;
     return per_sm * sms;
   }
-  static void attach(Ops *o) {
+  static void attach_phi(Ops *o) {
     o->phi_ring = phi;
-    o->s3_ring = s3;
-    o->max_blocks_s3_ring = max_blocks_s3;
     o->ring_lanes = G;
     o->ring_vec = V;
     o->ring_depth = R;
     o->ring_threads = T;
+  }
+  static void attach_s3(Ops *o) {
+    o->s3_ring = s3;
+    o->max_blocks_s3_ring = max_blocks_s3;
+    o->s3_lanes = G;
+    o->s3_vec = V;
+    o->s3_threads = T;
+  }
+  static void attach(Ops *o) {
+    attach_phi(o);
+    attach_s3(o);
   }
 };
 
@@ -181,7 +191,25 @@ void pick_ring(uint32_t k, Ops *o) {
   const int want_g = gsel ? atoi(gsel) : 0;
   const uint32_t ld = (k + 3u) & ~3u;
   if (k <= 32 || k > 256) return;
-  if (ld <= 112) {   // G = 8, V = ceil(ld/16)
+  if (ld <= 104 && ld > 56 && want_g != 8) {
+    // phi: G = 4, V = ceil(ld/8) in 8..13 -- eight neighbours per warp pass; at K = 100 the sweep is bound by
+    // the per-neighbour overhead, not by bytes (the state fits L2), and measured 1.5x the G = 8 tile.
+    // s3 : the G = 8 tile (its body is a plain row sum; G = 4 measured 1.5x SLOWER there)
+    switch ((ld + 7) / 8) {
+      case 8: RingTile<4, 8, 2, 128, SVI_RING_MINB>::attach_phi(o); break;
+      case 9: RingTile<4, 9, 2, 128, SVI_RING_MINB>::attach_phi(o); break;
+      case 10: RingTile<4, 10, 2, 128, SVI_RING_MINB>::attach_phi(o); break;
+      case 11: RingTile<4, 11, 2, 128, SVI_RING_MINB>::attach_phi(o); break;
+      case 12: RingTile<4, 12, 2, 128, SVI_RING_MINB>::attach_phi(o); break;
+      default: RingTile<4, 13, 2, 128, SVI_RING_MINB>::attach_phi(o); break;
+    }
+    switch ((ld + 15) / 16) {
+      case 4: RingTile<8, 4, 2, 256>::attach_s3(o); break;
+      case 5: RingTile<8, 5, 2, 256>::attach_s3(o); break;
+      case 6: RingTile<8, 6, 2, 256>::attach_s3(o); break;
+      default: RingTile<8, 7, 2, 256>::attach_s3(o); break;
+    }
+  } else if (ld <= 112) {   // G = 8, V = ceil(ld/16)
     switch ((ld + 15) / 16) {
       case 3: RingTile<8, 3, 2, 256>::attach(o); break;
       case 4: RingTile<8, 4, 2, 256>::attach(o); break;
@@ -434,12 +462,12 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   if (ops.s3_ring)
     h->blocks_s3 = (uint32_t)std::max<int64_t>(
         1, std::min<int64_t>(ops.max_blocks_s3_ring(h->sms, ld),
-                             ((int64_t)nseg3 * ops.ring_lanes + ops.ring_threads - 1) / ops.ring_threads));
+                             ((int64_t)nseg3 * ops.s3_lanes + ops.s3_threads - 1) / ops.s3_threads));
   else
     h->blocks_s3 = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ops.max_blocks_s3(h->sms),
                                                                    ((int64_t)nseg3 * ops.lanes + kThreads - 1) / kThreads));
   h->kpart_blocks = std::max(h->blocks_node, h->blocks_s3);
-  const size_t cap = std::max(2 * (size_t)ops.lanes * ops.vec, 2 * (size_t)ops.ring_lanes * ops.ring_vec);
+  const size_t cap = std::max(2 * (size_t)ops.lanes * ops.vec, 2 * (size_t)ops.s3_lanes * ops.s3_vec);
   cudaError_t e = cudaSuccess;
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   A(dalloc(&h->d_col, col.size(), &tot));
@@ -622,7 +650,7 @@ int svi_ls_phase_s3(svi_ls *h) {
   uint32_t cap3 = 2 * h->ops.lanes * h->ops.vec;
   if (h->ops.s3_ring) {
     h->ops.s3_ring(P, h->stream, h->blocks_s3);
-    cap3 = 2 * h->ops.ring_lanes * h->ops.ring_vec;
+    cap3 = 2 * h->ops.s3_lanes * h->ops.s3_vec;
   } else {
     h->ops.s3(P, h->stream, h->blocks_s3);
   }
