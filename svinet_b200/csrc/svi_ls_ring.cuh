@@ -343,12 +343,18 @@ __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P) {
       q_nxt = nxt_live ? __ldg(P.col + beg + c0 + G + lane) : p;
       qc_nxt = 0;
       const uint32_t ulim = min((uint32_t)G, cntmax - c0);
+#ifndef SVI_CONV_AT
+#define SVI_CONV_AT (G / 2)
+#endif
+      const uint32_t u_conv = min((uint32_t)(SVI_CONV_AT), ulim - 1u);
       // one copy of the body: unrolled G times with two phi_row instances each, the sweep is ~150 KB of
       // SASS and runs out of the instruction cache
 #pragma unroll 1
       for (uint32_t u = 0; u < ulim; ++u) {
         const uint32_t i = c0 + u;
-        if (u == 1 || ulim == 1) qc_nxt = nxt_live ? P.conv[q_nxt] : 0u;   // chunk c+1 flags, one row late
+        // chunk c+1 flags: half a chunk after their ids were requested (the id load is a DRAM miss of its own;
+        // one row later its result was still in flight: 9 % of the stall samples sat on this address)
+        if (u == u_conv) qc_nxt = nxt_live ? P.conv[q_nxt] : 0u;
         // control flow is warp-uniform here: full-mask shuffles, each confined to its G-lane segment
         const uint32_t q = __shfl_sync(0xffffffffu, q_cur, u, G);
         const uint32_t qc = __shfl_sync(0xffffffffu, qc_cur, u, G);
