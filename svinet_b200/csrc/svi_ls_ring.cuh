@@ -78,21 +78,6 @@ struct Ring {
 
 enum class Sweep { Phi, S3 };
 
-// fixed-shape pairwise tree over n values (latency log2(n) adds instead of n)
-template <int N>
-__device__ __forceinline__ double tree_sum(double (&t)[N]) {
-#pragma unroll
-  for (int n = N; n > 1; n = (n + 1) / 2) {
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) t[i] += t[n - 1 - i];
-  }
-  return t[0];
-}
-
-#ifndef SVI_PHI_VARIANT
-#define SVI_PHI_VARIANT 2   // 2 = two passes over the shared-memory row (default), 0 = weights kept in registers
-#endif
-#if SVI_PHI_VARIANT == 2
 // phi of one neighbour row sitting in shared memory at `rbase`, accumulated into acc (and the arg-max
 // community into mb).  `mask` is the shuffle mask: the full warp when every group of the warp is here,
 // the group's own lanes otherwise.
@@ -184,81 +169,6 @@ __device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_
   }
 }
 
-#else
-// phi of one neighbour row sitting in shared memory at `rbase`, accumulated into acc (and the arg-max
-// community into mb).  `mask` is the shuffle mask: the full warp when every group of the warp is here,
-// the group's own lanes otherwise.  The lane-local sum and arg-max are evaluated as trees: with two
-// resident warps per scheduler a 2V-deep dependent chain of FP64 compares is pure exposed latency.
-template <int G, int V, bool SPARSE, bool COMM>
-__device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_t lane, unsigned mask,
-                                        const double2 (&be)[V], double2 (&acc)[V], uint32_t &mb, bool sparse,
-                                        uint32_t p, uint32_t q) {
-  double2 w[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const double2 r = lds2(rbase + 16u * (lane + G * j));
-    w[j].x = be[j].x * r.x;
-    w[j].y = be[j].y * r.y;
-  }
-  if (SPARSE && sparse) {   // restrict to the union of the endpoints' active communities (:634-664)
-    const uint32_t *ap = P.abits + (size_t)p * P.words, *aq = P.abits + (size_t)q * P.words;
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const uint32_t c = 2u * (lane + G * j);
-      uint32_t bits = 0;
-      if (c < P.k) bits = (ap[c >> 5] | aq[c >> 5]) >> (c & 31u);
-      if (!(bits & 1u)) w[j].x = 0.0;
-      if (!(bits & 2u)) w[j].y = 0.0;
-    }
-  }
-  double t[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) t[j] = w[j].x + w[j].y;
-  double s = tree_sum<V>(t);
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(mask, s, o);
-  // s == 0 only for an empty active union: phi stays all-zero (:634-664 with an empty list).  No early
-  // return: other groups of the warp may share the shuffles below.
-  const double inv = s > 0.0 ? 1.0 / s : 0.0;
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    acc[j].x = fma(w[j].x, inv, acc[j].x);
-    acc[j].y = fma(w[j].y, inv, acc[j].y);
-  }
-  if (COMM) {
-    // arg-max of the unnormalised weights (same arg-max as phi = w/s); the FIRST maximum wins
-    // (D1Array::max, src/matrix.hh:521-532): a tournament over neighbours in column order, where the
-    // later entry replaces the earlier one only when strictly larger, keeps exactly that rule
-    double bv[V];
-    uint32_t be_[V];
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const bool y = w[j].y > w[j].x;
-      bv[j] = y ? w[j].y : w[j].x;
-      be_[j] = y ? 2 * j + 1 : 2 * j;
-    }
-#pragma unroll
-    for (int step = 1; step < V; step <<= 1) {
-#pragma unroll
-      for (int i = 0; i + step < V; i += 2 * step) {
-        const bool later = bv[i + step] > bv[i];
-        bv[i] = later ? bv[i + step] : bv[i];
-        be_[i] = later ? be_[i + step] : be_[i];
-      }
-    }
-    double best = bv[0];
-    uint32_t bestk = best > 0.0 ? 2u * (lane + G * (be_[0] >> 1)) + (be_[0] & 1u) : 0xffffffffu;
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(mask, best, o);
-      const uint32_t ok = __shfl_xor_sync(mask, bestk, o);
-      if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
-    }
-    if (best > 0.0 && lane == (bestk >> 5)) mb |= 1u << (bestk & 31u);
-  }
-}
-
-#endif
 
 // One group per segment, 32/G segments per warp in lockstep.
 //   MODE == Phi : part[seg] = sum over the segment's neighbours of phi        (K1, src/linksampling.cc:605-725)
