@@ -118,7 +118,7 @@ template <int G, int V, int R, int T, int MINB = 1>
 struct RingTile {
   static constexpr int GPB = T / G;
   static constexpr int CAP = 2 * G * V;
-  static constexpr size_t kSmem = (size_t)GPB * R * (CAP * 8 + 8);
+  static constexpr size_t kSmem = (size_t)GPB * R * (CAP * 8 + 8) + (size_t)GPB * CAP * 4;   // ring + barriers + one-hot tallies
   template <class K>
   static void prep(K kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);

@@ -78,6 +78,8 @@ struct Ring {
 
 enum class Sweep { Phi, S3 };
 
+__device__ __forceinline__ uint32_t grp_of(uint32_t tid, uint32_t g) { return tid / g; }
+
 // phi of one neighbour row sitting in shared memory at `rbase`, accumulated into acc (and the arg-max
 // community into mb).  `mask` is the shuffle mask: the full warp when every group of the warp is here,
 // the group's own lanes otherwise.
@@ -182,9 +184,13 @@ __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P) {
   const unsigned gmask = group_mask<G>();
   const uint32_t lane = threadIdx.x & (G - 1);
   const uint32_t grp = threadIdx.x / G;
-  // smem: [GPB][R] slots of CAP doubles (the tail beyond ld stays zero), then [GPB][R] mbarriers
+  // smem: [GPB][R] slots of CAP doubles (the tail beyond ld stays zero), then [GPB][R] mbarriers, then
+  // [GPB][CAP] u32 tallies of the one-hot (shortcut) links per column
   const uint32_t rows0 = smem_u32(smem_raw);
   const uint32_t bars0 = rows0 + GPB * R * CAP * 8u;
+  uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw + (size_t)GPB * R * (CAP * 8u + 8u)) + grp_of(threadIdx.x, G) * CAP;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(GPB * CAP); i += T)
+    reinterpret_cast<uint32_t *>(smem_raw + (size_t)GPB * R * (CAP * 8u + 8u))[i] = 0u;
   Ring<R> ring;
   ring.row_bytes = P.ld * 8u;
   ring.slot_bytes = CAP * 8u;
@@ -288,15 +294,8 @@ __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P) {
           } else if (live) {
             if (pc) {          // s3[pc-1] += mphi[q][pc]  (sic, :739-740; column K reads as 0)
               one_hot += pc < P.k ? P.mphi[(size_t)q * P.ld + pc] : 0.0;
-            } else {           // s3[qc-1] += mphi[p][qc]  (:741-742)
-              const double v = qc < P.k ? self_row[qc] : 0.0;
-              const uint32_t c = qc - 1u;
-#pragma unroll
-              for (int j = 0; j < V; ++j) {
-                const uint32_t c2 = 2u * (lane + G * j);
-                if (c == c2) s3acc[j].x += v;
-                if (c == c2 + 1u) s3acc[j].y += v;
-              }
+            } else {           // s3[qc-1] += mphi[p][qc]  (:741-742): the same addend for every such
+              if (lane == 0) hist[qc - 1u]++;   // neighbour, so only counted here and applied once per segment
             }
           }
         } else {
@@ -305,13 +304,9 @@ __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P) {
           if (full) {
             phi_row<G, V, SPARSE, COMM>(P, rbase, lane, allfull ? 0xffffffffu : gmask, be, acc, mb, sparse, p, q);
           } else if (live) {
-            const uint32_t c = (pc ? pc : qc) - 1u;   // one-hot phi, :622-631
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-              const uint32_t c2 = 2u * (lane + G * j);
-              if (c == c2) acc[j].x += 1.0;
-              if (c == c2 + 1u) acc[j].y += 1.0;
-            }
+            // one-hot phi, :622-631: counted per column in shared memory (one lane, one RMW) instead of a
+            // 2V-wide compare-and-add by every lane; the counts join acc once per segment
+            if (lane == 0) hist[(pc ? pc : qc) - 1u]++;
           }
         }
         // refill this slot with neighbour i+R (its id sits in the current or the next chunk)
@@ -324,11 +319,17 @@ __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P) {
       }
     }
 
+    __syncwarp();   // lane 0's tallies -> every lane
     if (MODE == Sweep::Phi) {
       if (have) {
         double *out = P.part + (size_t)seg * P.ld;
 #pragma unroll
-        for (int j = 0; j < V; ++j) st_row2(out, 2u * (lane + G * j), P.ld, acc[j]);
+        for (int j = 0; j < V; ++j) {
+          const uint2 h = *reinterpret_cast<const uint2 *>(hist + 2u * (lane + G * j));
+          acc[j].x += (double)h.x;     // exact: integers, same as the reference's repeated += 1
+          acc[j].y += (double)h.y;
+          st_row2(out, 2u * (lane + G * j), P.ld, acc[j]);
+        }
         if (COMM && mb) atomicOr(P.mbits + (size_t)p * P.words + lane, mb);
       }
     } else if (have) {
@@ -340,7 +341,18 @@ __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P) {
         s3acc[j].y = fma(mp.y, acc[j].y, s3acc[j].y);
         if (pc && pc - 1u == c) s3acc[j].x += one_hot;
         if (pc && pc - 1u == c + 1u) s3acc[j].y += one_hot;
+        // neighbours converged to community c (resp. c+1): count x mphi[p][c+1] (resp. [c+2]), sic (Q4);
+        // column K reads as 0
+        uint2 *hp = reinterpret_cast<uint2 *>(hist + c);
+        const uint2 h = *hp;
+        if (h.x | h.y) {
+          const double vx = c + 1u < P.k ? self_row[c + 1u] : 0.0, vy = c + 2u < P.k ? self_row[c + 2u] : 0.0;
+          s3acc[j].x = fma((double)h.x, vx, s3acc[j].x);
+          s3acc[j].y = fma((double)h.y, vy, s3acc[j].y);
+          *hp = make_uint2(0u, 0u);   // this group's next segment starts from zero
+        }
       }
+      __syncwarp(gmask);   // (`have` differs between the groups of a warp: group mask, not the full warp)
     }
   }
   if (MODE == Sweep::S3) {
