@@ -201,3 +201,29 @@ def test_fa2_resume_from_saved_model(cli):
         want_l = np.array([[float(x) for x in l.split("\t")[1:]] for l in golden_text("fa2_c1_m200", "lambda.txt").strip().split("\n")])
         assert np.array_equal(gam, want_g) and np.array_equal(lam, want_l)
         assert os.path.isdir(os.path.join(d, "n75-k4-resumed-Srnode"))
+
+
+def test_fa2_load_heldout_file_and_single_nodes(cli):
+    """-rnode -stratified -load-validation <file> (FastAMM2::load_heldout, fastamm2.cc:267-299) on a graph padded
+    with single nodes: the pairs of the file (external ids, either order) become the held-out set, and no RNG
+    draw is spent on it (the shuffled order and the initial gamma stay those of a run without held-out draw)."""
+    with Scratch() as d:
+        lines = ["1\t2", "2\t3", "3\t4", "4\t5", "5\t1", "1\t3", "2\t5", "6\t7", "7\t8", "8\t6", "6\t1", "9\t2"]
+        open(os.path.join(d, "g.txt"), "w").write("\n".join(lines) + "\n")
+        open(os.path.join(d, "held.txt"), "w").write("3\t1\n7\t6\n4\t9\n")       # two links, one non-link
+        dump = os.path.join(d, "dump"); os.makedirs(dump)
+        subprocess.check_call([cli, "-file", "g.txt", "-n", "11", "-k", "3", "-rnode", "-stratified", "-load-validation",
+                               "held.txt", "-dump-init", dump], cwd=d, stdout=subprocess.DEVNULL)
+        held = np.fromfile(os.path.join(dump, "heldout.u32"), dtype=np.uint32).reshape(-1, 2)
+        g = orc.Graph.read(os.path.join(d, "g.txt"), 11)
+        assert (g.n, g.singles) == (9, 2)
+        id2seq = {int(g.seq2id[i]): i for i in range(g.n)}
+        want = [tuple(sorted((id2seq[a], id2seq[b]))) for a, b in ((3, 1), (7, 6), (4, 9))]
+        assert [tuple(r) for r in held.tolist()] == want
+        gamma = np.fromfile(os.path.join(dump, "gamma.f64")).reshape(-1, 3)
+        assert gamma.shape == (9, 3) and np.all(gamma > 0)
+        out = os.path.join(d, "n11-k3-mmsb-Srnode")             # named after the -n ARGUMENT, like the reference
+        seq2id = [int(x) for x in g.seq2id[:g.n]]
+        want_txt = "".join("%d\t%d\n" % (seq2id[a], seq2id[b]) for a, b in want) + "\n"
+        assert open(os.path.join(out, "heldout-pairs.txt")).read() == want_txt
+        g.close()
