@@ -543,7 +543,7 @@ void LinkSampling::infer() {
   bool write_comm = false;
   const uint32_t rf = (uint32_t)env_.reportfreq;
   Lap lap;
-  double t_step = 0, t_report = 0;
+  double t_step = 0, t_report = 0, t_heldout = 0;
   auto since = [](std::chrono::steady_clock::time_point a) {
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
   };
@@ -553,8 +553,8 @@ void LinkSampling::infer() {
       env_.plog("maxiterations reached", true);
       env_.terminate = true;
       if (lap.on)
-        fprintf(stderr, "[linksampling] %u iterations: device steps %.3f s, reports (held-out + communities.txt) %.3f s\n",
-                iter_, t_step, t_report);
+        fprintf(stderr, "[linksampling] %u iterations: device steps %.3f s, reports %.3f s (held-out %.3f s, communities.txt %.3f s)\n",
+                iter_, t_step, t_report, t_heldout, t_report - t_heldout);
       lap("iterations");
       do_on_stop();
       lap("do_on_stop (writers)");
@@ -580,6 +580,7 @@ void LinkSampling::infer() {
         exit(0);
       }
       test_likelihood_line();
+      t_heldout += since(t0);
       log_communities();
       t_report += since(t0);
     }
