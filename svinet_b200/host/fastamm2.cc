@@ -1,6 +1,7 @@
 // fastamm2.cc -- see fastamm2.hh.  All file:line citations refer to the reference's src/fastamm2.cc unless
 // another file is named.
 #include "fastamm2.hh"
+#include "fixed_fmt.hh"
 
 #include <algorithm>
 #include <cerrno>
@@ -394,7 +395,7 @@ void FastAMM2::save_model() {
     s.clear();
     s.append(b, (size_t)snprintf(b, sizeof b, "%d\t%d\t", i, net_.seq2id(i)));
     const double *g = &gamma_[(size_t)i * k_];
-    for (uint32_t c = 0; c < k_; ++c) s.append(b, (size_t)snprintf(b, sizeof b, c == k_ - 1 ? "%.5f\n" : "%.5f\t", g[c]));
+    for (uint32_t c = 0; c < k_; ++c) append_fixed(s, g[c], 5, c == k_ - 1 ? '\n' : '\t');
     fwrite(s.data(), 1, s.size(), gf);
   }
   fclose(gf);
@@ -425,7 +426,7 @@ void FastAMM2::compute_and_log_groups() {
     const double *pi_i = &epi[(size_t)i * k_];
     double max = .0;
     for (uint32_t j = 0; j < k_; ++j) {
-      s.append(b, (size_t)snprintf(b, sizeof b, "%.3f\t", pi_i[j]));
+      append_fixed(s, pi_i[j], 3, '\t');
       if (pi_i[j] > max) { max = pi_i[j]; groups[i] = j; }
     }
     for (uint32_t m : net_.get_edges(i)) {

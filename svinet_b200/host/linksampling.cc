@@ -1,6 +1,7 @@
 // linksampling.cc -- see linksampling.hh.  All file:line citations refer to the reference's
 // src/linksampling.cc unless another file is named.
 #include "linksampling.hh"
+#include "fixed_fmt.hh"
 
 #include <algorithm>
 #include <cassert>
@@ -60,11 +61,6 @@ struct Lap {
   }
 };
 
-inline void append_fmt(std::string &s, const char *fmt, double v) {
-  char b[64];
-  const int len = snprintf(b, sizeof b, fmt, v);
-  s.append(b, (size_t)len);
-}
 
 }  // namespace
 
@@ -450,7 +446,7 @@ void LinkSampling::save_model() {
     char b[48];
     s.append(b, (size_t)snprintf(b, sizeof b, "%d\t%d\t", i, net_.seq2id(i)));
     const double *g = &gamma_[(size_t)i * k];
-    for (uint32_t c = 0; c < k; ++c) append_fmt(s, c == k - 1 ? "%.5f\n" : "%.5f\t", g[c]);
+    for (uint32_t c = 0; c < k; ++c) append_fixed(s, g[c], 5, c == k - 1 ? '\n' : '\t');
   });
   fclose(gf);
   FILE *lf = open_or_die(env_.file("/lambda.txt"), "w", "lambda");
@@ -467,7 +463,7 @@ void LinkSampling::write_groups() {
     const double *g = &gamma_[(size_t)i * k];
     double sum = .0;
     for (uint32_t c = 0; c < k; ++c) sum += g[c];
-    for (uint32_t c = 0; c < k; ++c) append_fmt(s, c == k - 1 ? "%.3f\n" : "%.3f\t", g[c] / sum);
+    for (uint32_t c = 0; c < k; ++c) append_fixed(s, g[c] / sum, 3, c == k - 1 ? '\n' : '\t');
   });
   fclose(f);
 }
