@@ -2,6 +2,7 @@
 // src/linksampling.cc unless another file is named.
 #include "linksampling.hh"
 #include "fixed_fmt.hh"
+#include "pool.hh"
 
 #include <algorithm>
 #include <cassert>
@@ -10,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <sstream>
 #include <thread>
 
@@ -260,48 +263,59 @@ void LinkSampling::init_gamma2() {
   const unsigned nt = std::max(1u, std::min(16u, std::min<unsigned>(std::thread::hardware_concurrency(),
                                                                     (unsigned)(nl / 4096 + 1))));
   std::vector<double> buf[2] = {std::vector<double>(chunk * k), std::vector<double>(chunk * k)};
-  auto work = [&](const double *u0, size_t l0, size_t cnt) {
-    double *u = const_cast<double *>(u0);
-    std::vector<std::thread> th;
-    // phase A
-    for (unsigned t = 0; t < nt; ++t)
-      th.emplace_back([&, t] {
-        for (size_t i = cnt * t / nt; i < cnt * (t + 1) / nt; ++i) {
-          double *phi = u + i * k;
-          double s = .0;
-          for (uint32_t c = 0; c < k; ++c) s += phi[c];
-          for (uint32_t c = 0; c < k; ++c) phi[c] = phi[c] / s;
-        }
-      });
-    for (auto &x : th) x.join();
-    th.clear();
-    // phase B
-    for (unsigned t = 0; t < nt; ++t)
-      th.emplace_back([&, t] {
-        const uint32_t v0 = (uint32_t)((uint64_t)n_ * t / nt), v1 = (uint32_t)((uint64_t)n_ * (t + 1) / nt);
-        for (size_t i = 0; i < cnt; ++i) {
-          const uint32_t p = lp[l0 + i], q = lq[l0 + i];
-          const double *phi = u + i * k;
-          if (p >= v0 && p < v1) { double *g = &gamma_[(size_t)p * k]; for (uint32_t c = 0; c < k; ++c) g[c] += phi[c]; }
-          if (q >= v0 && q < v1) { double *g = &gamma_[(size_t)q * k]; for (uint32_t c = 0; c < k; ++c) g[c] += phi[c]; }
-        }
-      });
-    for (auto &x : th) x.join();
+  Pool pool(nt);
+  auto work = [&](double *u, size_t l0, size_t cnt) {
+    pool.run([&](unsigned t) {                       // phase A
+      for (size_t i = cnt * t / nt; i < cnt * (t + 1) / nt; ++i) {
+        double *phi = u + i * k;
+        double s = .0;
+        for (uint32_t c = 0; c < k; ++c) s += phi[c];
+        for (uint32_t c = 0; c < k; ++c) phi[c] = phi[c] / s;
+      }
+    });
+    pool.run([&](unsigned t) {                       // phase B
+      const uint32_t v0 = (uint32_t)((uint64_t)n_ * t / nt), v1 = (uint32_t)((uint64_t)n_ * (t + 1) / nt);
+      for (size_t i = 0; i < cnt; ++i) {
+        const uint32_t p = lp[l0 + i], q = lq[l0 + i];
+        const double *phi = u + i * k;
+        if (p >= v0 && p < v1) { double *g = &gamma_[(size_t)p * k]; for (uint32_t c = 0; c < k; ++c) g[c] += phi[c]; }
+        if (q >= v0 && q < v1) { double *g = &gamma_[(size_t)q * k]; for (uint32_t c = 0; c < k; ++c) g[c] += phi[c]; }
+      }
+    });
   };
-  // double-buffered: the generator fills chunk i+1 while the workers consume chunk i
-  size_t l0 = 0;
-  int cur = 0;
-  size_t cnt = std::min(chunk, nl);
-  rng_.uniform_fill(buf[cur].data(), cnt * k);
-  while (l0 < nl) {
-    const size_t next_l0 = l0 + cnt, next_cnt = std::min(chunk, nl - next_l0);
-    std::thread producer([&] { if (next_cnt) rng_.uniform_fill(buf[cur ^ 1].data(), next_cnt * k); });
-    work(buf[cur].data(), l0, cnt);
-    producer.join();
-    l0 = next_l0;
-    cnt = next_cnt;
-    cur ^= 1;
+  // double-buffered: one producer thread fills chunk i+1 with the generator while the pool consumes chunk i
+  std::mutex m;
+  std::condition_variable cv;
+  size_t produced = 0, consumed = 0;       // chunks
+  const size_t nchunks = (nl + chunk - 1) / chunk;
+  std::thread producer([&] {
+    for (size_t c = 0; c < nchunks; ++c) {
+      {
+        std::unique_lock<std::mutex> g(m);
+        cv.wait(g, [&] { return c < consumed + 2; });     // at most two chunks ahead of the consumer
+      }
+      const size_t cnt = std::min(chunk, nl - c * chunk);
+      rng_.uniform_fill(buf[c & 1].data(), cnt * k);
+      {
+        std::lock_guard<std::mutex> g(m);
+        produced = c + 1;
+      }
+      cv.notify_all();
+    }
+  });
+  for (size_t c = 0; c < nchunks; ++c) {
+    {
+      std::unique_lock<std::mutex> g(m);
+      cv.wait(g, [&] { return produced > c; });
+    }
+    work(buf[c & 1].data(), c * chunk, std::min(chunk, nl - c * chunk));
+    {
+      std::lock_guard<std::mutex> g(m);
+      consumed = c + 1;
+    }
+    cv.notify_all();
   }
+  producer.join();
 }
 
 int LinkSampling::load_model() {
