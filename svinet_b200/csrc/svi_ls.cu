@@ -623,6 +623,7 @@ int svi_ls_phase_phi(svi_ls *h, uint32_t iter, int write_comm) {
   if (!h) return fail(SVI_ERR_INVALID, "null handle");
   DeviceGuard guard(h->device);
   const Params &P = h->P;
+  h->conv_snap_valid = false;   // a new iteration: a snapshot left by an unfinished refresh/lambda pair is stale
   if (write_comm)  // _communities.clear(); _fmap.zero()  (src/linksampling.cc:584-587)
     CK(cudaMemsetAsync(h->d_mbits, 0, (size_t)P.n * P.words * sizeof(uint32_t), h->stream));
   if (h->ops.phi_ring) h->ops.phi_ring(P, h->stream, iter > 1000 && P.k_div10 > 0, write_comm != 0);
