@@ -42,7 +42,10 @@ CASES = {
                     "n1000-k28-mmsb-linksampling"),
     "c2_m12": ("ca-AstroPh.csv", 17903, 20, ["-max-iterations", "12", "-no-stop"], "n17903-k20-mmsb-linksampling"),
     "c2_m25": ("ca-AstroPh.csv", 17903, 20, ["-max-iterations", "25", "-no-stop"], "n17903-k20-mmsb-linksampling"),
+    # the natural run: the validation stop ends it (iteration 30 here); small files only
+    "c2_natural": ("ca-AstroPh.csv", 17903, 20, [], "n17903-k20-mmsb-linksampling"),
 }
+KEEP_ONLY = {"c2_natural": ["lambda.txt", "communities.txt", "validation.txt", "max.txt", "validation-edges.txt", "param.txt"]}
 
 # `-rnode -stratified` (class FastAMM2): name -> (input, n, k, flags, outdir)
 FA2_CASES = {
@@ -97,7 +100,7 @@ def main():
         shutil.rmtree(dst, ignore_errors=True)
         os.makedirs(dst)
         entry = {"input": fname, "n": n, "k": k, "flags": flags, "outdir": outdir, "md5": {}, "mode": mode}
-        for f in keep:
+        for f in KEEP_ONLY.get(name, keep):
             p = os.path.join(src, f)
             if not os.path.exists(p):
                 continue

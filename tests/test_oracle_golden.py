@@ -77,6 +77,9 @@ def test_oracle_matches_reference_small(case):
 @pytest.mark.parametrize("case", SLOW)
 def test_oracle_matches_reference_astroph(case):
     rep = _run_case(case)
+    if "gamma.txt" not in rep:        # c2_natural keeps the small files only: the stop iteration is the point
+        assert golden_text(case, "max.txt").split("\t")[0] == "30" and rep["max.txt"][1] == 0 and rep["lambda.txt"][1] <= 1
+        return
     nf, noff = rep["gamma.txt"]
     assert nf == 17903 * 22
     assert noff <= nf // 10000, rep
