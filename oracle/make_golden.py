@@ -42,6 +42,8 @@ CASES = {
                     "n1000-k28-mmsb-linksampling"),
     "c2_m12": ("ca-AstroPh.csv", 17903, 20, ["-max-iterations", "12", "-no-stop"], "n17903-k20-mmsb-linksampling"),
     "c2_m25": ("ca-AstroPh.csv", 17903, 20, ["-max-iterations", "25", "-no-stop"], "n17903-k20-mmsb-linksampling"),
+    "c1_etasparse_m10": ("assort-75-4.txt", 75, 4, ["-max-iterations", "10", "-no-stop", "-eta-type", "sparse"],
+                         "n75-k4-mmsb-linksampling"),
     # the natural run: the validation stop ends it (iteration 30 here); small files only
     "c2_natural": ("ca-AstroPh.csv", 17903, 20, [], "n17903-k20-mmsb-linksampling"),
 }

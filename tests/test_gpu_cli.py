@@ -35,7 +35,7 @@ def run_case(cli, case, d):
 
 
 @pytest.mark.parametrize("case", ["c1_m30", "c1_natural", "c1_m1", "c1_seed7_m12", "c1_accuracy_m8", "c1_k7_m15",
-                                  "lfr_k28_m20", "c2_m12", "c2_m25", "c2_natural"])  # the -link-sampling fixtures
+                                  "lfr_k28_m20", "c2_m12", "c2_m25", "c2_natural", "c1_etasparse_m10"])  # the -link-sampling fixtures
 def test_cli_output_directory_matches_reference(cli, case):
     with Scratch() as d:
         ent, out = run_case(cli, case, d)

@@ -86,7 +86,8 @@ def run_model_lockstep(g, k, sweeps, tol=TOL, **opts):
 
 # ---- the reference's own inputs (configs 1-2 of BASELINE.json and the LFR example) -------------
 @pytest.mark.parametrize("case,sweeps", [("c1_m30", 31), ("c1_k7_m15", 16), ("c1_seed7_m12", 13),
-                                         ("c1_accuracy_m8", 9), ("c1_m1", 2), ("lfr_k28_m20", 21)])
+                                         ("c1_accuracy_m8", 9), ("c1_m1", 2), ("lfr_k28_m20", 21),
+                                         ("c1_etasparse_m10", 11)])
 def test_lockstep_small_inputs(case, sweeps):
     ent = MANIFEST[case]
     opts = {"max_iterations": 0, "use_validation_stop": 0}
@@ -96,6 +97,8 @@ def test_lockstep_small_inputs(case, sweeps):
         opts["accuracy"] = 1
     if case == "c1_m1":
         opts["max_iterations"] = 1
+    if "-eta-type" in ent["flags"]:
+        opts["eta0"], opts["eta1"] = {"sparse": (0.97, 6.33)}[ent["flags"][ent["flags"].index("-eta-type") + 1]]
     with Scratch() as d:
         g = orc.Graph.read(input_path(ent["input"], d), ent["n"])
         worst = run_model_lockstep(g, ent["k"], sweeps, **opts)

@@ -52,10 +52,13 @@ def oracle_opts(flags):
         o["seed"] = float(flags[flags.index("-seed") + 1])
     if "-accuracy" in flags:
         o["accuracy"] = 1
+    if "-eta-type" in flags:
+        o["eta0"], o["eta1"] = {"sparse": (0.97, 6.33), "dense": (4700.59, 0.77)}[flags[flags.index("-eta-type") + 1]]
     return o
 
 
-@pytest.mark.parametrize("case", ["c1_m30", "c1_seed7_m12", "c1_accuracy_m8", "c1_k7_m15", "lfr_k28_m20"])
+@pytest.mark.parametrize("case", ["c1_m30", "c1_seed7_m12", "c1_accuracy_m8", "c1_k7_m15", "lfr_k28_m20",
+                                  "c1_etasparse_m10"])
 def test_startup_state_is_bit_identical_to_oracle(cli, case):
     with Scratch() as d:
         ent, got = run_dump(cli, case, d)

@@ -27,6 +27,9 @@ def _flags_to_opts(flags):
             o["seed"] = float(flags[i + 1]); i += 1
         elif f == "-accuracy":
             o["accuracy"] = 1
+        elif f == "-eta-type":                      # network.cc:233-250
+            o["eta0"], o["eta1"] = {"uniform": (1.0, 1.0), "sparse": (0.97, 6.33), "dense": (4700.59, 0.77)}[flags[i + 1]]
+            i += 1
         else:
             raise KeyError(f)
         i += 1
