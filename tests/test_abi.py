@@ -55,6 +55,19 @@ def test_fa2_header_symbols_all_exported(lib):
     assert lib.svi_fa2_step(None, 0, 0, 0, 0, None) == -1
 
 
+def test_abi_is_usable_from_plain_c(lib, tmp_path):
+    """include/*.h are C headers and libsvi_ls.so links from C: tests/cc/abi_c_check.c with gcc -std=c99."""
+    import subprocess
+    exe = str(tmp_path / "abi_c_check")
+    libdir = os.path.dirname(svbuild.LIB)
+    subprocess.check_call([os.environ.get("CC", "gcc"), "-std=c99", "-Wall", "-Werror", "-pedantic", "-I",
+                           os.path.join(REPO, "include"), "-o", exe, os.path.join(REPO, "tests", "cc", "abi_c_check.c"),
+                           "-L", libdir, "-lsvi_ls", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "svi_ls_create rc=" in out.stdout
+
+
 def test_abi_version(lib):
     assert lib.svi_ls_abi_version() == 1
 
