@@ -2,6 +2,7 @@
 // another file is named.
 #include "fastamm2.hh"
 #include "fixed_fmt.hh"
+#include "textio.hh"
 
 #include <algorithm>
 #include <cerrno>
@@ -261,45 +262,9 @@ void FastAMM2::init_lambda() {
 }
 
 int FastAMM2::load_model() {
-  const std::string gpath = env_.gamma_location + "gamma.txt", lpath = env_.gamma_location + "lambda.txt";
-  FILE *gf = fopen(gpath.c_str(), "r");
-  if (!gf) { fprintf(stderr, "no gamma.txt found\n"); return -1; }
-  std::vector<char> line(32 * (size_t)k_ + 64);
-  uint32_t rows = 0;
-  while (fgets(line.data(), (int)line.size(), gf)) {
-    char *p = line.data();
-    uint32_t col = 0;
-    for (;;) {
-      char *q = nullptr;
-      const double d = strtod(p, &q);
-      if (q == p) break;
-      p = q;
-      if (col >= 2 && col - 2 < k_ && rows < n_) gamma_[(size_t)rows * k_ + col - 2] = d;
-      col++;
-    }
-    if (col < k_ + 1) { fprintf(stderr, "error parsing gamma file\n"); return -1; }
-    rows++;
-  }
-  fclose(gf);
-  if (rows != n_) { fprintf(stderr, "gamma.txt has %u rows, expected %u\n", rows, n_); return -1; }
-  FILE *lf = fopen(lpath.c_str(), "r");
-  if (!lf) { fprintf(stderr, "no lambda.txt found\n"); return -1; }
-  rows = 0;
-  while (fgets(line.data(), (int)line.size(), lf)) {
-    char *p = line.data();
-    uint32_t col = 0;
-    for (;;) {
-      char *q = nullptr;
-      const double d = strtod(p, &q);
-      if (q == p) break;
-      p = q;
-      if (col >= 1 && col - 1 < 2 && rows < k_) lambda_[(size_t)rows * 2 + col - 1] = d;
-      col++;
-    }
-    rows++;
-  }
-  fclose(lf);
-  if (rows != k_) { fprintf(stderr, "lambda.txt has %u rows, expected %u\n", rows, k_); return -1; }
+  // <dir>gamma.txt: "seq \t id \t g_0 .. g_K-1"; <dir>lambda.txt: "k \t l_0 \t l_1"  
+  if (load_numeric_rows(env_.gamma_location + "gamma.txt", n_, k_, 2, gamma_.data(), "gamma.txt") < 0) return -1;
+  if (load_numeric_rows(env_.gamma_location + "lambda.txt", k_, 2, 1, lambda_.data(), "lambda.txt") < 0) return -1;
   return 0;
 }
 

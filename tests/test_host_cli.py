@@ -230,3 +230,30 @@ def test_fa2_load_heldout_file_and_single_nodes(cli):
         want_txt = "".join("%d\t%d\n" % (seq2id[a], seq2id[b]) for a, b in want) + "\n"
         assert open(os.path.join(out, "heldout-pairs.txt")).read() == want_txt
         g.close()
+
+
+def test_link_sampling_resume_from_saved_model_text(cli):
+    """-link-sampling -load <dir/> (linksampling.cc:1267-1352) through the threaded loader: starts from exactly the
+    %.5f text of the reference's own gamma.txt / lambda.txt (fixture c2_m25: 17 903 rows); a truncated file is an
+    error, not a partial load."""
+    ent = MANIFEST["c2_m25"]
+    with Scratch() as d:
+        inp = input_path(ent["input"], d)
+        if not os.path.exists(os.path.join(d, ent["input"])):
+            os.symlink(inp, os.path.join(d, ent["input"]))
+        saved = os.path.join(d, "saved"); os.makedirs(saved)
+        gtxt, ltxt = golden_text("c2_m25", "gamma.txt"), golden_text("c2_m25", "lambda.txt")
+        open(os.path.join(saved, "gamma.txt"), "w").write(gtxt)
+        open(os.path.join(saved, "lambda.txt"), "w").write(ltxt)
+        dump = os.path.join(d, "dump"); os.makedirs(dump)
+        base = [cli, "-file", ent["input"], "-n", "17903", "-k", "20", "-link-sampling", "-label", "resumed"]
+        subprocess.check_call(base + ["-load", "saved/", "-dump-init", dump], cwd=d, stdout=subprocess.DEVNULL)
+        gam = np.fromfile(os.path.join(dump, "gamma.f64")).reshape(17903, 20)
+        want = np.array([[float(x) for x in l.split("\t")[2:]] for l in gtxt.strip().split("\n")])
+        assert np.array_equal(gam, want)
+        lam = np.fromfile(os.path.join(dump, "lambda.f64")).reshape(20, 2)
+        assert np.array_equal(lam, np.array([[float(x) for x in l.split("\t")[1:]] for l in ltxt.strip().split("\n")]))
+        # truncated gamma.txt
+        open(os.path.join(saved, "gamma.txt"), "w").write("\n".join(gtxt.strip().split("\n")[:-5]) + "\n")
+        p = subprocess.run(base + ["-load", "saved/", "-dump-init", dump], cwd=d, capture_output=True)
+        assert p.returncode != 0 and b"rows" in p.stderr
