@@ -150,15 +150,3 @@ class Fa2Engine:
         i = Fa2Info()
         _check(self.L, self.L.svi_fa2_get_info(self.h, C.byref(i)))
         return {f: getattr(i, f) for f, _ in Fa2Info._fields_}
-
-
-# ---- host replay of the device's minibatch stream (tests; mirrors k_fa2_draw) -------------------------
-def philox4x32_10(counter, key):
-    c = [int(x) & 0xffffffff for x in counter]
-    k0, k1 = int(key[0]) & 0xffffffff, int(key[1]) & 0xffffffff
-    for _ in range(10):
-        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
-        c = [((p1 >> 32) ^ c[1] ^ k0) & 0xffffffff, p1 & 0xffffffff, ((p0 >> 32) ^ c[3] ^ k1) & 0xffffffff,
-             p0 & 0xffffffff]
-        k0, k1 = (k0 + 0x9E3779B9) & 0xffffffff, (k1 + 0xBB67AE85) & 0xffffffff
-    return c
