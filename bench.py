@@ -151,6 +151,61 @@ def step_bytes_survey(nlinks, n, k, s=8):
     return nlinks * (6 * k * s + 16) + 7 * n * k * s
 
 
+def verify_sampled_rows(step_once, get_state, get_converged, n, k, links, alpha, sample=512, seed=99):
+    """Parity spot-check AT THE BENCHMARKED SIZE: run one more iteration (annealing off, tally on) and recompute
+    the new gamma rows of `sample` random nodes on the host in the REFERENCE's formulation -- Elogpi = psi(gamma) -
+    psi(sum gamma) with scipy's digamma (independent of both the device's and the oracle's), per link the running
+    log-sum-exp of src/linksampling.cc:685-694 and exp(phi - r) (src/matrix.hh:320-325), the one-hot shortcut of
+    :619-631, then compute_mean_indicators (:526-545) -- from the state downloaded before the iteration.
+    A stale / wrong neighbour row shifts a gamma row by O(1/degree); the bar is 1e-9 relative."""
+    from scipy.special import digamma
+    rng = np.random.default_rng(seed)
+    deg = np.bincount(links.ravel().astype(np.int64), minlength=n)
+    cand = np.flatnonzero(deg > 0)
+    pick = np.sort(rng.choice(cand, size=min(sample, cand.size), replace=False))
+    is_s = np.zeros(n, dtype=bool)
+    is_s[pick] = True
+    m0, m1 = is_s[links[:, 0]], is_s[links[:, 1]]
+    src = np.concatenate([links[m0, 0], links[m1, 1]]).astype(np.int64)
+    dst = np.concatenate([links[m0, 1], links[m1, 0]]).astype(np.int64)
+    rows = np.unique(np.concatenate([src, dst]))
+    g0, lam0 = get_state()
+    gr = g0[rows].copy()
+    del g0
+    conv0 = get_converged().astype(np.int64)
+    step_once()
+    g1, _ = get_state()
+    got = g1[pick].copy()
+    del g1
+    elogpi = digamma(gr) - digamma(gr.sum(1, keepdims=True))
+    elogbeta0 = digamma(lam0[:, 0]) - digamma(lam0.sum(1))
+    si, di = np.searchsorted(rows, src), np.searchsorted(rows, dst)
+    pc, qc = conv0[src], conv0[dst]
+    short = (pc != 0) != (qc != 0)
+    full = ~short
+    ep, eq = elogpi[si[full]], elogpi[di[full]]
+    r = None
+    with np.errstate(over="ignore"):
+        for kk in range(k):
+            x = ep[:, kk] + eq[:, kk] + elogbeta0[kk]
+            r = x if kk == 0 else np.where(x < r, r + np.log(1 + np.exp(x - r)),
+                                           x + np.log(1 + np.exp(r - x)))
+    phi = np.exp(ep + eq + elogbeta0[None, :] - r[:, None]) if full.any() else np.zeros((0, k))
+    out_idx = np.searchsorted(pick, src)
+    acc = np.zeros((pick.size, k))
+    np.add.at(acc, out_idx[full], phi)
+    np.add.at(acc, (out_idx[short], np.where(pc[short] != 0, pc[short], qc[short]) - 1), 1.0)
+    tl = 2.0 * deg[pick].astype(np.float64)[:, None]
+    gn = alpha + acc
+    mphi = (gn - alpha) / tl
+    want = gn + (n - tl - 1.0) * mphi
+    err = float(np.max(np.abs(got - want) / np.abs(want)))
+    return {"rows": int(pick.size), "half_edges": int(src.size), "shortcut_half_edges": int(short.sum()),
+            "max_rel_err": err, "tol": 1e-9, "ok": bool(err <= 1e-9),
+            "what": "gamma rows of sampled nodes after one more iteration (annealing off) vs a host recomputation in "
+                    "the reference's formulation (scipy digamma, running log-sum-exp per link, compute_mean_indicators)"}
+
+
 # --------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -290,6 +345,14 @@ def run_ours(args):
         e2e = runner.e2e(step_fn=step, it0=it, steps=max(1, min(args.steps, 5)), nlinks=nlinks, unit=UNIT,
                          heldout=heldout_pairs(n, links, max(2, min(nlinks // 100, 2_000_000))))
 
+    verify = None
+    if world == 1 and not args.no_verify:
+        t0 = time.time()
+        verify = verify_sampled_rows(lambda: eng.step(it, False, True), eng.get_state,
+                                     lambda: eng.get_converged()[0], n, k, links, 1.0 / k)
+        verify["seconds"] = time.time() - t0
+        it += 1
+
     if rank != 0:
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
@@ -320,6 +383,7 @@ def run_ours(args):
                      "note": "pull-form bytes of this kernel (DESIGN.md section 4)",
                      "step_gbs_survey_8d_formula": survey_gbs,
                      "step_frac_survey_8d_formula": survey_gbs / peak},
+        "verify": verify,
         "setup_s": {"generate": t_gen, "create+upload": t_create},
         "wall_s_timed_region": t_wall,
     }
@@ -472,6 +536,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="(default on at 1 GPU) recompute sampled gamma rows on the host")
+    ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the --impl reference arm")
     ap.add_argument("--path", default="ls", choices=["ls", "fa2"],
