@@ -75,6 +75,11 @@ void       orc_prune(orc_state *s);                                             
  * (clear .. prune).  `iter` is the reference's _iter (only used for the >1000 test, :634). */
 void orc_step(orc_state *s, uint32_t iter, int annealing, int write_comm);
 
+/* the same sweep over `threads` host cores (OpenMP; oracle_ls_omp.c): timing baseline, equal to orc_step up to the
+ * summation order; dense + shortcut branches only (iter <= 1000).  threads < 1 = all. */
+void orc_step_omp(orc_state *s, int annealing, int write_comm, int threads);
+int  orc_omp_max_threads(void);
+
 /* held-out log-likelihood of one pair, linksampling.hh:259-292 (literal O(K^2) non-link form) */
 double orc_edge_likelihood(const orc_state *s, uint32_t p, uint32_t q, int y, double epsilon);
 

@@ -39,9 +39,21 @@ inline void append_fixed(std::string &s, double v, int decimals, char tail = 0) 
       return;
     }
   }
-  int len = snprintf(b, sizeof b - 1, "%.*f", decimals, v);
-  if (tail) b[len++] = tail;
-  s.append(b, (size_t)len);
+  // slow path: boundary cases, non-finite values, huge magnitudes (DBL_MAX prints 309 digits before the point;
+  // gamma can get there in the annealing phase when a starved community's sum[k] is ~0, src/linksampling.cc:541-542)
+  char big[352];
+  int len = snprintf(big, sizeof big - 1, "%.*f", decimals, v);
+  if (len < 0) len = 0;
+  if (len > (int)sizeof big - 2) {                 // cannot happen for a double; never index past the buffer
+    std::string wide((size_t)len + 1, '\0');
+    snprintf(&wide[0], wide.size(), "%.*f", decimals, v);
+    wide.resize((size_t)len);
+    s += wide;
+    if (tail) s.push_back(tail);
+    return;
+  }
+  if (tail) big[len++] = tail;
+  s.append(big, (size_t)len);
 }
 
 #endif

@@ -156,8 +156,10 @@ LinkSampling::LinkSampling(Env &env, Network &network)
   lap("svi_ls_create + set_state");
 
   // held-out pairs in std::map<Edge,bool> order (lexicographic), the order validation_likelihood sums in
+  // (the reference holds them in a map: a -load-validation file that repeats a pair still counts it once)
   validation_sorted_ = validation_pairs_;
   std::sort(validation_sorted_.begin(), validation_sorted_.end());
+  validation_sorted_.erase(std::unique(validation_sorted_.begin(), validation_sorted_.end()), validation_sorted_.end());
   for (const Edge &e : validation_sorted_) {
     hp_.push_back(e.first);
     hq_.push_back(e.second);

@@ -14,7 +14,7 @@ int main() {
   auto check = [&](double v, int d) {
     std::string s;
     append_fixed(s, v, d, '\t');
-    char b[64];
+    char b[400];
     snprintf(b, sizeof b, "%.*f\t", d, v);
     if (s != b) {
       if (bad < 10) printf("MISMATCH d=%d v=%.17g ours=%s ref=%s\n", d, v, s.c_str(), b);
@@ -32,7 +32,8 @@ int main() {
       check(std::nextafter(t, 1e300), d);
     }
     for (double v : {0.0, -0.0, 1e-300, -1e-300, 0.5, 1.5, 2.5, 0.125, 0.0625, 1e14, 9.99999e14, 1e15, 1e22, -1e15, 0.000005,
-                     0.0000049999999, 1.0 / 0.0, -1.0 / 0.0, std::nan("")})
+                     0.0000049999999, 1e41, -1e41, 3.3e47, 1e100, 1e300, -1e300, 1.7976931348623157e308,
+                     -1.7976931348623157e308, 1.0 / 0.0, -1.0 / 0.0, std::nan("")})
       check(v, d);
   }
   printf("%ld checks, %ld mismatches\n", n, bad);

@@ -64,7 +64,8 @@ def lib():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(
-            os.path.getmtime(os.path.join(ORACLE_DIR, f)) for f in ("oracle_ls.c", "oracle_fa2.c", "oracle_fa2.h")):
+            os.path.getmtime(os.path.join(ORACLE_DIR, f)) for f in ("oracle_ls.c", "oracle_fa2.c", "oracle_fa2.h",
+                                                                     "oracle_ls_omp.c", "oracle_ls.h")):
         build()
     L = C.CDLL(LIB_PATH)
     L.orc_graph_read.restype = C.POINTER(OrcGraph)
@@ -80,6 +81,8 @@ def lib():
     L.orc_set_dir_exp.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.orc_prune.argtypes = [C.POINTER(OrcState)]
     L.orc_step.argtypes = [C.POINTER(OrcState), C.c_uint32, C.c_int, C.c_int]
+    L.orc_step_omp.argtypes = [C.POINTER(OrcState), C.c_int, C.c_int, C.c_int]
+    L.orc_omp_max_threads.restype = C.c_int
     L.orc_edge_likelihood.restype = C.c_double
     L.orc_edge_likelihood.argtypes = [C.POINTER(OrcState), C.c_uint32, C.c_uint32, C.c_int, C.c_double]
     L.orc_digamma.restype = C.c_double
@@ -224,6 +227,9 @@ class State:
 
     def step(self, it, annealing, write_comm):
         lib().orc_step(self.ptr, it, int(annealing), int(write_comm))
+
+    def step_omp(self, annealing, write_comm, threads=0):
+        lib().orc_step_omp(self.ptr, int(annealing), int(write_comm), int(threads))
 
     def refresh_expectations(self):
         s = self.c

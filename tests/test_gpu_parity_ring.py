@@ -78,28 +78,29 @@ def test_ring_sweeps_long_segments_hub_and_converged(k):
     st.free()
 
 
-@pytest.mark.parametrize("k", [100, 200])
-def test_ring_sweep_active_set_branch_long_segments(k):
-    """iter > 1000 with concentrated rows (both endpoints < K/10 active communities) at ring tilings and
-    long segments: the SPARSE instantiation of k_sweep_ring."""
+@pytest.mark.parametrize("k", [20, 40, 64, 100, 200])
+def test_active_set_branch_on_a_settled_state(k):
+    """iter > 1000 (:634-681) on a state where the branch really fires: the oracle first runs 20 sweeps from a
+    random start, so that many rows have settled on < K/10 active communities (a random concentrated state loses
+    its concentration in one sweep, and the branch would silently never run).  Ring tilings with long segments for
+    K > 32 (the SPARSE instantiation of k_sweep_ring), k_phi<SPARSE> for K = 20."""
     n = 1500
     links = dense_graph_with_hub(n, k, 120, seed=400 + k)
-    rng = np.random.default_rng(3 * k)
-    gamma = 1.0 / k + 1e-3 * rng.random((n, k))
-    for p in range(n):
-        hot = rng.choice(k, size=rng.integers(0, k // 10 + 3), replace=False)
-        gamma[p, hot] += 2.0 + 5 * rng.random(hot.size)
-    st = oracle_state(n, k, links, gamma, np.ones((k, 2)))
-    orc.lib().orc_prune(st.ptr)
-    st.arr("converged")[:] = 0
+    gamma, lam = synth.random_state(n, k, links, seed=k)
+    st = oracle_state(n, k, links, gamma, lam)
+    for it in range(20):
+        st.step_omp(it < 10, 0, 0)           # all-cores oracle leg: only used to reach a settled state quickly
     eng = engine_from_state(st, links.shape[0], seg_len=256)
-    assert eng.info()["ring_depth"] > 0
-    st.step(5, 0, 0); eng.step(5, 0, 0)
+    assert (eng.info()["ring_depth"] > 0) == (k > 32)
+    st.step(20, 0, 0); eng.step(20, 0, 0)    # one ordinary sweep from the same start brings the device's masks in line
     compare_sweep(eng, st, "warm")
-    for it, wc in [(1001, 1), (1002, 0)]:
+    sparse = dense = 0
+    for it, wc in [(1001, 1), (1002, 0), (1003, 1)]:
         st.step(it, 0, wc); eng.step(it, 0, wc)
         compare_sweep(eng, st, "k=%d iter %d" % (k, it), check_member=bool(wc))
-    assert st.c.cnt_sparse > 0
+        sparse += st.c.cnt_sparse
+        dense += st.c.cnt_dense
+    assert sparse > 0 and dense > 0, (sparse, dense)
     eng.close(); st.free()
 
 
