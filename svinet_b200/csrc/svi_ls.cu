@@ -7,6 +7,7 @@
 #include "svi_common.h"
 #include "svi_ls_kernels.cuh"
 #include "svi_ls_ring.cuh"
+#include "svi_ls_build.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -41,10 +42,13 @@ using svi::g_err;
   } while (0)
 
 using svi::Params;
+using svi::s3_owner;
 
 // launchers for one (G, V, LOGDOM) tiling
 struct Ops {
-  void (*phi)(const Params &, cudaStream_t, bool sparse, bool comm);
+  // phi sweep over segments [seg_first, seg_end); comm: with the link-community tally; publish: the tally also sets the
+  // neighbour's bit (one arg-max per link)
+  void (*phi)(const Params &, cudaStream_t, bool sparse, bool comm, uint32_t seg_first, uint32_t seg_end, uint32_t publish);
   void (*node)(const Params &, cudaStream_t, uint32_t blocks);
   void (*s3)(const Params &, cudaStream_t, uint32_t blocks);
   void (*lambda)(const Params &, cudaStream_t, int annealing, int update);
@@ -55,8 +59,11 @@ struct Ops {
   int (*max_blocks_s3)(int sms);
   int lanes, vec, logdom;
   // second-generation sweeps (svi_ls_ring.cuh), present for 32 < K <= 256
-  void (*phi_ring)(const Params &, cudaStream_t, bool sparse, bool comm) = nullptr;
+  void (*phi_ring)(const Params &, cudaStream_t, bool sparse, bool comm, uint32_t seg_first, uint32_t seg_end,
+                   uint32_t publish) = nullptr;
   void (*s3_ring)(const Params &, cudaStream_t, uint32_t blocks) = nullptr;
+  void (*prepare_phi_ring)() = nullptr;   // per-device function attributes (dynamic shared memory), once per handle
+  void (*prepare_s3_ring)() = nullptr;
   int (*max_blocks_s3_ring)(int sms, uint32_t ld) = nullptr;
   int ring_lanes = 0, ring_vec = 0, ring_depth = 0, ring_threads = 256;   // tiling of phi_ring
   int s3_lanes = 0, s3_vec = 0, s3_threads = 256;                         // tiling of s3_ring (may differ)
@@ -69,13 +76,13 @@ struct Tile {
   static constexpr int CAP = 2 * G * V;
   static constexpr size_t kSmem = (size_t)(kThreads / G) * CAP * sizeof(double);
 
-  static void phi(const Params &P, cudaStream_t st, bool sparse, bool comm) {
-    if (!P.nseg) return;
-    const uint32_t blocks = (uint32_t)(((uint64_t)P.nseg * G + kThreads - 1) / kThreads);
-    if (sparse && comm) svi::k_phi<G, V, L, true, true><<<blocks, kThreads, 0, st>>>(P);
-    else if (sparse) svi::k_phi<G, V, L, true, false><<<blocks, kThreads, 0, st>>>(P);
-    else if (comm) svi::k_phi<G, V, L, false, true><<<blocks, kThreads, 0, st>>>(P);
-    else svi::k_phi<G, V, L, false, false><<<blocks, kThreads, 0, st>>>(P);
+  static void phi(const Params &P, cudaStream_t st, bool sparse, bool comm, uint32_t s0, uint32_t s1, uint32_t pub) {
+    if (s1 <= s0) return;
+    const uint32_t blocks = (uint32_t)(((uint64_t)(s1 - s0) * G + kThreads - 1) / kThreads);
+    if (sparse && comm) svi::k_phi<G, V, L, true, true><<<blocks, kThreads, 0, st>>>(P, s0, s1, pub);
+    else if (sparse) svi::k_phi<G, V, L, true, false><<<blocks, kThreads, 0, st>>>(P, s0, s1, pub);
+    else if (comm) svi::k_phi<G, V, L, false, true><<<blocks, kThreads, 0, st>>>(P, s0, s1, pub);
+    else svi::k_phi<G, V, L, false, false><<<blocks, kThreads, 0, st>>>(P, s0, s1, pub);
   }
   static void node(const Params &P, cudaStream_t st, uint32_t blocks) {
     svi::k_node<G, V><<<blocks, kThreads, kSmem, st>>>(P);
@@ -123,29 +130,28 @@ struct RingTile {
   static void prep(K kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
   }
-  static void phi(const Params &P, cudaStream_t st, bool sparse, bool comm) {
-    if (!P.nseg) return;
-    const uint32_t blocks = (uint32_t)(((uint64_t)P.nseg * G + T - 1) / T);
-    using svi::Sweep;
-#define SVI_RING_PHI(S, C)                                                         \
-  do {                                                                             \
-    auto kern = svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, S, C>;                   \
-    prep(kern);                                                                    \
-    kern<<<blocks, T, kSmem, st>>>(P);                                             \
-  } while (0)
-    if (sparse && comm) SVI_RING_PHI(true, true);
-    else if (sparse) SVI_RING_PHI(true, false);
-    else if (comm) SVI_RING_PHI(false, true);
-    else SVI_RING_PHI(false, false);
-#undef SVI_RING_PHI
+  using Sweep = svi::Sweep;
+  static void prepare_phi() {
+    prep(svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, false, false>);
+    prep(svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, false, true>);
+    prep(svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, true, false>);
+    prep(svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, true, true>);
+  }
+  static void prepare_s3() { prep(svi::k_sweep_ring<G, V, R, T, MINB, Sweep::S3, false, false>); }
+  static void phi(const Params &P, cudaStream_t st, bool sparse, bool comm, uint32_t s0, uint32_t s1, uint32_t pub) {
+    if (s1 <= s0) return;
+    const uint32_t blocks = (uint32_t)(((uint64_t)(s1 - s0) * G + T - 1) / T);
+    if (sparse && comm) svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, true, true><<<blocks, T, kSmem, st>>>(P, s0, s1, pub);
+    else if (sparse) svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, true, false><<<blocks, T, kSmem, st>>>(P, s0, s1, pub);
+    else if (comm) svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, false, true><<<blocks, T, kSmem, st>>>(P, s0, s1, pub);
+    else svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, false, false><<<blocks, T, kSmem, st>>>(P, s0, s1, pub);
   }
   static void s3(const Params &P, cudaStream_t st, uint32_t blocks) {
-    auto kern = svi::k_sweep_ring<G, V, R, T, MINB, svi::Sweep::S3, false, false>;
-    prep(kern);
-    kern<<<blocks, T, kSmem, st>>>(P);
+    if (P.nseg <= P.nseg_lo) return;
+    svi::k_sweep_ring<G, V, R, T, MINB, Sweep::S3, false, false><<<blocks, T, kSmem, st>>>(P, P.nseg_lo, P.nseg, 0u);
   }
   static int max_blocks_s3(int sms, uint32_t) {
-    auto kern = svi::k_sweep_ring<G, V, R, T, MINB, svi::Sweep::S3, false, false>;
+    auto kern = svi::k_sweep_ring<G, V, R, T, MINB, Sweep::S3, false, false>;
     prep(kern);
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, kSmem) != cudaSuccess || per_sm < 1)
@@ -154,6 +160,7 @@ struct RingTile {
   }
   static void attach_phi(Ops *o) {
     o->phi_ring = phi;
+    o->prepare_phi_ring = prepare_phi;
     o->ring_lanes = G;
     o->ring_vec = V;
     o->ring_depth = R;
@@ -161,6 +168,7 @@ struct RingTile {
   }
   static void attach_s3(Ops *o) {
     o->s3_ring = s3;
+    o->prepare_s3_ring = prepare_s3;
     o->max_blocks_s3_ring = max_blocks_s3;
     o->s3_lanes = G;
     o->s3_vec = V;
@@ -280,8 +288,11 @@ struct svi_ls {
   uint64_t he_phi = 0, he_s3 = 0, device_bytes = 0;
   uint32_t seg_len = 0;
   // owned device memory
-  uint32_t *d_col = nullptr, *d_seg_node = nullptr, *d_seg_beg = nullptr, *d_seg_cnt = nullptr;
-  uint32_t *d_node_seg_off = nullptr, *d_seg3_node = nullptr, *d_seg3_beg = nullptr, *d_seg3_cnt = nullptr;
+  uint32_t *d_col = nullptr, *d_seg_node = nullptr, *d_seg_beg = nullptr, *d_seg_cnt = nullptr, *d_seg_nnc = nullptr;
+  uint32_t *d_node_seg_lo = nullptr, *d_node_seg_up = nullptr, *d_conv_dirty = nullptr;
+  bool force_partition = false;
+  bool shard = false;            // the handle owns a proper node block of the graph
+  bool partition_every_sweep = false;   // converged flags of other shards arrive by exchange: no local dirty flag
   double *d_tl = nullptr, *d_b = nullptr, *d_mphi = nullptr, *d_gamma = nullptr, *d_gacc = nullptr;
   double *d_part = nullptr, *d_kvec = nullptr, *d_kpart = nullptr, *d_lambda = nullptr, *d_eb = nullptr;
   double *d_scale = nullptr, *d_stage = nullptr;
@@ -307,8 +318,8 @@ struct DeviceGuard {
 };
 
 void free_all(svi_ls *h) {
-  void *ptrs[] = {h->d_col, h->d_seg_node, h->d_seg_beg, h->d_seg_cnt, h->d_node_seg_off, h->d_seg3_node,
-                  h->d_seg3_beg, h->d_seg3_cnt, h->d_tl, h->d_b, h->d_mphi, h->d_gamma, h->d_gacc, h->d_part,
+  void *ptrs[] = {h->d_col, h->d_seg_node, h->d_seg_beg, h->d_seg_cnt, h->d_seg_nnc, h->d_node_seg_lo,
+                  h->d_node_seg_up, h->d_conv_dirty, h->d_tl, h->d_b, h->d_mphi, h->d_gamma, h->d_gacc, h->d_part,
                   h->d_kvec, h->d_kpart, h->d_lambda, h->d_eb, h->d_scale, h->d_stage, h->d_conv, h->d_active,
                   h->d_abits, h->d_mbits, h->d_conv_snap};
   for (void *p : ptrs)
@@ -323,15 +334,6 @@ int ensure_stage(svi_ls *h, size_t elems) {
   CK(cudaMalloc((void **)&h->d_stage, std::max<size_t>(elems, 1) * sizeof(double)));
   h->stage_elems = elems;
   return SVI_OK;
-}
-
-// Which endpoint sweeps a link in the s3 pass.  The pass is symmetric in its endpoints (src/linksampling.cc:
-// 731-746: the full product commutes, and the shortcut always reads "the other endpoint's row at the converged
-// endpoint's community"), so any rule works; the parity rule gives every contiguous node block about half of
-// its links, whereas "the smaller id owns" hands the low blocks of a sharded run most of the s3 work.
-inline uint32_t s3_owner(uint32_t p, uint32_t q) {
-  const uint32_t lo = std::min(p, q), hi = std::max(p, q);
-  return ((lo ^ hi) & 1u) ? lo : hi;
 }
 
 // balanced split of `deg` neighbours into chunks of at most seg_len
@@ -389,51 +391,100 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   const uint32_t n = cfg->n, k = cfg->k, nb = cfg->node_begin, ne = cfg->node_end;
   const uint32_t nlocal = ne - nb, ld = (k + 3u) & ~3u, words = (k + 31u) / 32u;
   h->nlocal = nlocal;
-
-  // ---- CSR of the shard's half-edges; the neighbours a node OWNS for the s3 sweep are stored last ----
-  std::vector<uint32_t> deg_lo(nlocal, 0), deg_up(nlocal, 0);
-  std::vector<double> tl_host(n, 0.0);
-  for (uint64_t e = 0; e < cfg->nlinks; ++e) {
-    const uint32_t p = links[2 * e], q = links[2 * e + 1];
-    if (p >= n || q >= n || p == q) {
-      delete h;
-      return fail(SVI_ERR_INVALID, "svi_ls_create: link %llu = (%u,%u) out of range", (unsigned long long)e, p, q);
-    }
-    const uint32_t own = s3_owner(p, q), oth = own == p ? q : p;
-    if (own >= nb && own < ne) deg_up[own - nb]++;
-    if (oth >= nb && oth < ne) deg_lo[oth - nb]++;
-    tl_host[p] += 2.0;   // Q3: both adjacency directions count each link for both endpoints
-    tl_host[q] += 2.0;
-  }
-  if (tl) std::copy(tl, tl + n, tl_host.begin());
-  std::vector<uint64_t> off(nlocal + 1, 0);
-  for (uint32_t v = 0; v < nlocal; ++v) off[v + 1] = off[v] + deg_lo[v] + deg_up[v];
-  const uint64_t he = off[nlocal];
-  if (he > 0xffffffffull) {
+  h->shard = nb != 0 || ne != n;
+  h->partition_every_sweep = h->shard;
+  if (n >= 0x80000000u) {
     delete h;
-    return fail(SVI_ERR_UNSUPPORTED, "svi_ls_create: %llu half-edges exceed the 32-bit CSR of one shard",
-                (unsigned long long)he);
+    return fail(SVI_ERR_UNSUPPORTED, "svi_ls_create: n=%u exceeds the 31-bit node ids of the CSR build", n);
   }
-  std::vector<uint32_t> col(std::max<uint64_t>(he, 1));
+
+  // ---- CSR of the shard's half-edges, built on the device (svi_ls_build.cuh); the neighbours a node OWNS for
+  //      the s3 sweep are stored last in its list ----
+  std::vector<uint32_t> deg_lo(nlocal, 0), deg_up(nlocal, 0);
+  uint64_t he = 0, he3 = 0;
   {
-    std::vector<uint64_t> cur_lo(nlocal), cur_up(nlocal);
-    for (uint32_t v = 0; v < nlocal; ++v) {
-      cur_lo[v] = off[v];
-      cur_up[v] = off[v] + deg_lo[v];
+    const uint64_t nl = cfg->nlinks;
+    uint32_t *d_links = nullptr, *d_dlo = nullptr, *d_dup = nullptr;
+    uint64_t *d_keys = nullptr, *d_keys2 = nullptr;
+    unsigned long long *d_err = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    auto release = [&]() {
+      for (void *q : {(void *)d_links, (void *)d_dlo, (void *)d_dup, (void *)d_keys, (void *)d_keys2, (void *)d_err, d_tmp})
+        if (q) cudaFree(q);
+    };
+    A(cudaMalloc((void **)&d_links, std::max<uint64_t>(nl, 1) * 2 * sizeof(uint32_t)));
+    A(cudaMalloc((void **)&d_keys, std::max<uint64_t>(nl, 1) * 2 * sizeof(uint64_t)));
+    A(cudaMalloc((void **)&d_keys2, std::max<uint64_t>(nl, 1) * 2 * sizeof(uint64_t)));
+    A(cudaMalloc((void **)&d_dlo, std::max<uint32_t>(nlocal, 1) * sizeof(uint32_t)));
+    A(cudaMalloc((void **)&d_dup, std::max<uint32_t>(nlocal, 1) * sizeof(uint32_t)));
+    A(cudaMalloc((void **)&d_err, 2 * sizeof(unsigned long long)));
+    int end_bit = 34;
+    while (end_bit < 64 && ((uint64_t)nlocal >> (end_bit - 33)) != 0) ++end_bit;
+    cub::DoubleBuffer<uint64_t> dbuf(d_keys, d_keys2);
+    if (e == cudaSuccess) A(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, dbuf, (int64_t)(2 * nl), 0, end_bit));
+    A(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 1)));
+    if (e == cudaSuccess) {
+      A(cudaMemcpy(d_links, links, nl * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      A(cudaMemset(d_dlo, 0, std::max<uint32_t>(nlocal, 1) * sizeof(uint32_t)));
+      A(cudaMemset(d_dup, 0, std::max<uint32_t>(nlocal, 1) * sizeof(uint32_t)));
+      A(cudaMemset(d_err, 0, 2 * sizeof(unsigned long long)));
     }
-    for (uint64_t e = 0; e < cfg->nlinks; ++e) {
-      const uint32_t p = links[2 * e], q = links[2 * e + 1];
-      const uint32_t own = s3_owner(p, q), oth = own == p ? q : p;
-      if (own >= nb && own < ne) col[cur_up[own - nb]++] = oth;
-      if (oth >= nb && oth < ne) col[cur_lo[oth - nb]++] = own;
+    unsigned long long err[2] = {0, 0};
+    if (e == cudaSuccess && nl) {
+      svi::k_build_keys<<<h->sms * 8, 256>>>(d_links, nl, n, nb, ne, d_keys, d_dlo, d_dup, d_err);
+      A(cudaGetLastError());
+      A(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, dbuf, (int64_t)(2 * nl), 0, end_bit));
+    }
+    if (e == cudaSuccess) {
+      A(cudaMemcpy(err, d_err, sizeof err, cudaMemcpyDeviceToHost));
+      A(cudaMemcpy(deg_lo.data(), d_dlo, nlocal * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      A(cudaMemcpy(deg_up.data(), d_dup, nlocal * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    if (e == cudaSuccess && err[0]) {
+      release();
+      delete h;
+      const uint64_t bad = err[1];
+      return fail(SVI_ERR_INVALID, "svi_ls_create: link %llu = (%u,%u) out of range (%llu such links)",
+                  (unsigned long long)bad, links[2 * bad], links[2 * bad + 1], err[0]);
+    }
+    for (uint32_t v = 0; v < nlocal; ++v) {
+      he += (uint64_t)deg_lo[v] + deg_up[v];
+      he3 += deg_up[v];
+    }
+    if (e == cudaSuccess && he > 0xffffffffull) {
+      release();
+      delete h;
+      return fail(SVI_ERR_UNSUPPORTED, "svi_ls_create: %llu half-edges exceed the 32-bit CSR of one shard",
+                  (unsigned long long)he);
+    }
+    if (e == cudaSuccess) {
+      A(dalloc(&h->d_col, he, &h->device_bytes));
+      if (e == cudaSuccess && he) {
+        svi::k_keys_to_col<<<h->sms * 8, 256>>>(dbuf.Current(), he, h->d_col);
+        A(cudaGetLastError());
+        A(cudaDeviceSynchronize());
+      }
+    }
+    release();
+    if (e != cudaSuccess) {
+      const int rc = fail(e == cudaErrorMemoryAllocation ? SVI_ERR_NOMEM : SVI_ERR_CUDA, "svi_ls_create (graph build): %s",
+                          cudaGetErrorString(e));
+      free_all(h);
+      delete h;
+      return rc;
     }
   }
-  uint64_t he3 = 0;
-  for (uint32_t v = 0; v < nlocal; ++v) he3 += deg_up[v];
   h->he_phi = he;
   h->he_s3 = he3;
+  std::vector<double> tl_host(n, 0.0);
+  if (tl) std::copy(tl, tl + n, tl_host.begin());
+  else   // Q3: both adjacency directions count each link for both endpoints.  A shard knows its own nodes' degrees,
+    for (uint32_t v = 0; v < nlocal; ++v) tl_host[nb + v] = 2.0 * ((double)deg_lo[v] + deg_up[v]);   // and reads no others
 
-  // ---- work segments ----
+  // ---- work segments: every node's "lo" part and "up" (owned) part are cut separately ----
   uint32_t seg_len = cfg->seg_len;
   if (!seg_len) {
     // enough segments to fill the machine several times over, long enough to amortise the
@@ -442,17 +493,29 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
     seg_len = 256;
     while (seg_len > 16 && he / seg_len < target) seg_len >>= 1;
   }
+  seg_len = std::min(seg_len, svi::kMaxSegLen);
   h->seg_len = seg_len;
-  std::vector<uint32_t> sn, sb, sc, s3n, s3b, s3c, nso(nlocal + 1, 0);
-  sn.reserve(he / seg_len + nlocal);
-  sb.reserve(he / seg_len + nlocal);
-  sc.reserve(he / seg_len + nlocal);
-  for (uint32_t v = 0; v < nlocal; ++v) {
-    push_segments(nb + v, (uint32_t)off[v], deg_lo[v] + deg_up[v], seg_len, sn, sb, sc);
-    nso[v + 1] = (uint32_t)sn.size();
-    push_segments(nb + v, (uint32_t)(off[v] + deg_lo[v]), deg_up[v], seg_len, s3n, s3b, s3c);
+  std::vector<uint32_t> sn, sb, sc, nlo(nlocal + 1, 0), nup(nlocal + 1, 0);
+  sn.reserve(he / seg_len + 2 * (size_t)nlocal);
+  sb.reserve(he / seg_len + 2 * (size_t)nlocal);
+  sc.reserve(he / seg_len + 2 * (size_t)nlocal);
+  {
+    uint64_t at = 0;
+    for (uint32_t v = 0; v < nlocal; ++v) {
+      push_segments(nb + v, (uint32_t)at, deg_lo[v], seg_len, sn, sb, sc);
+      nlo[v + 1] = (uint32_t)sn.size();
+      at += (uint64_t)deg_lo[v] + deg_up[v];
+    }
+    const uint32_t nseg_lo = (uint32_t)sn.size();
+    at = 0;
+    nup[0] = nseg_lo;
+    for (uint32_t v = 0; v < nlocal; ++v) {
+      push_segments(nb + v, (uint32_t)(at + deg_lo[v]), deg_up[v], seg_len, sn, sb, sc);
+      nup[v + 1] = (uint32_t)sn.size();
+      at += (uint64_t)deg_lo[v] + deg_up[v];
+    }
   }
-  const uint32_t nseg = (uint32_t)sn.size(), nseg3 = (uint32_t)s3n.size();
+  const uint32_t nseg_lo = nlo[nlocal], nseg = (uint32_t)sn.size(), nseg3 = nseg - nseg_lo;
 
   // ---- device memory ----
   uint64_t &tot = h->device_bytes;
@@ -466,18 +529,19 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   else
     h->blocks_s3 = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ops.max_blocks_s3(h->sms),
                                                                    ((int64_t)nseg3 * ops.lanes + kThreads - 1) / kThreads));
+  if (ops.prepare_phi_ring) ops.prepare_phi_ring();
+  if (ops.prepare_s3_ring) ops.prepare_s3_ring();
   h->kpart_blocks = std::max(h->blocks_node, h->blocks_s3);
   const size_t cap = std::max(2 * (size_t)ops.lanes * ops.vec, 2 * (size_t)ops.s3_lanes * ops.s3_vec);
   cudaError_t e = cudaSuccess;
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-  A(dalloc(&h->d_col, col.size(), &tot));
   A(dalloc(&h->d_seg_node, nseg, &tot));
   A(dalloc(&h->d_seg_beg, nseg, &tot));
   A(dalloc(&h->d_seg_cnt, nseg, &tot));
-  A(dalloc(&h->d_node_seg_off, nlocal + 1, &tot));
-  A(dalloc(&h->d_seg3_node, nseg3, &tot));
-  A(dalloc(&h->d_seg3_beg, nseg3, &tot));
-  A(dalloc(&h->d_seg3_cnt, nseg3, &tot));
+  A(dalloc(&h->d_seg_nnc, nseg, &tot));
+  A(dalloc(&h->d_node_seg_lo, nlocal + 1, &tot));
+  A(dalloc(&h->d_node_seg_up, nlocal + 1, &tot));
+  A(dalloc(&h->d_conv_dirty, 1, &tot));
   A(dalloc(&h->d_tl, n, &tot));
   A(dalloc(&h->d_b, nld, &tot));
   A(dalloc(&h->d_mphi, nld, &tot));
@@ -497,14 +561,12 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
     if (bytes) A(cudaMemcpy(d, s, bytes, cudaMemcpyHostToDevice));
   };
   if (e == cudaSuccess) {
-    H2D(h->d_col, col.data(), he * sizeof(uint32_t));
     H2D(h->d_seg_node, sn.data(), nseg * sizeof(uint32_t));
     H2D(h->d_seg_beg, sb.data(), nseg * sizeof(uint32_t));
     H2D(h->d_seg_cnt, sc.data(), nseg * sizeof(uint32_t));
-    H2D(h->d_node_seg_off, nso.data(), (nlocal + 1) * sizeof(uint32_t));
-    H2D(h->d_seg3_node, s3n.data(), nseg3 * sizeof(uint32_t));
-    H2D(h->d_seg3_beg, s3b.data(), nseg3 * sizeof(uint32_t));
-    H2D(h->d_seg3_cnt, s3c.data(), nseg3 * sizeof(uint32_t));
+    H2D(h->d_seg_nnc, sc.data(), nseg * sizeof(uint32_t));   // nobody has converged: every neighbour is "not converged"
+    H2D(h->d_node_seg_lo, nlo.data(), (nlocal + 1) * sizeof(uint32_t));
+    H2D(h->d_node_seg_up, nup.data(), (nlocal + 1) * sizeof(uint32_t));
     H2D(h->d_tl, tl_host.data(), n * sizeof(double));
   }
   if (e != cudaSuccess) {
@@ -521,9 +583,10 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   P.alpha = cfg->alpha; P.eta0 = cfg->eta0; P.eta1 = cfg->eta1; P.ones_d = (double)cfg->ones;
   P.k_div10 = k / 10;
   P.col = h->d_col;
-  P.seg_node = h->d_seg_node; P.seg_beg = h->d_seg_beg; P.seg_cnt = h->d_seg_cnt; P.nseg = nseg;
-  P.node_seg_off = h->d_node_seg_off;
-  P.seg3_node = h->d_seg3_node; P.seg3_beg = h->d_seg3_beg; P.seg3_cnt = h->d_seg3_cnt; P.nseg3 = nseg3;
+  P.seg_node = h->d_seg_node; P.seg_beg = h->d_seg_beg; P.seg_cnt = h->d_seg_cnt; P.seg_nnc = h->d_seg_nnc;
+  P.nseg = nseg; P.nseg_lo = nseg_lo;
+  P.node_seg_lo = h->d_node_seg_lo; P.node_seg_up = h->d_node_seg_up;
+  P.conv_dirty = h->d_conv_dirty;
   P.tl = h->d_tl;
   P.b = h->d_b; P.mphi = h->d_mphi; P.gamma = h->d_gamma; P.gacc = h->d_gacc; P.part = h->d_part;
   P.kvec = h->d_kvec; P.kpart = h->d_kpart; P.lambda = h->d_lambda; P.eb = h->d_eb; P.scale = h->d_scale;
@@ -604,6 +667,7 @@ int svi_ls_set_converged(svi_ls *h, const uint32_t *converged) {
   DeviceGuard guard(h->device);
   CK(cudaMemcpyAsync(h->d_conv, converged, (size_t)h->P.n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  h->force_partition = true;   // arbitrary flags (a resume may even clear some): rebuild every segment's partition
   return SVI_OK;
 }
 
@@ -624,10 +688,29 @@ int svi_ls_phase_phi(svi_ls *h, uint32_t iter, int write_comm) {
   DeviceGuard guard(h->device);
   const Params &P = h->P;
   h->conv_snap_valid = false;   // a new iteration: a snapshot left by an unfinished refresh/lambda pair is stale
+  // the ring sweeps read neighbour lists partitioned by the converged flags (svi_ls_ring.cuh: k_partition); nodes
+  // converge in k_refresh, at the end of the previous iteration
+  if ((h->ops.phi_ring || h->ops.s3_ring) && P.nseg) {
+    const bool force = h->force_partition || h->partition_every_sweep;
+    svi::k_partition<<<(uint32_t)std::min<uint64_t>((P.nseg + 7) / 8, (uint64_t)h->sms * 8), 256, 0, h->stream>>>(P, force);
+    CK(cudaMemsetAsync(h->d_conv_dirty, 0, sizeof(uint32_t), h->stream));
+    h->force_partition = false;
+  }
   if (write_comm)  // _communities.clear(); _fmap.zero()  (src/linksampling.cc:584-587)
     CK(cudaMemsetAsync(h->d_mbits, 0, (size_t)P.n * P.words * sizeof(uint32_t), h->stream));
-  if (h->ops.phi_ring) h->ops.phi_ring(P, h->stream, iter > 1000 && P.k_div10 > 0, write_comm != 0);
-  else h->ops.phi(P, h->stream, iter > 1000 && P.k_div10 > 0, write_comm != 0);
+  auto phi = h->ops.phi_ring ? h->ops.phi_ring : h->ops.phi;
+  const bool sparse = iter > 1000 && P.k_div10 > 0;
+  if (!write_comm) {
+    phi(P, h->stream, sparse, false, 0, P.nseg, 0);
+  } else if (h->shard) {
+    // a shard holds the membership words of its own nodes only: the arg-max is taken on both sides of a link
+    phi(P, h->stream, sparse, true, 0, P.nseg, 0);
+  } else {
+    // one arg-max per LINK (src/linksampling.cc:704-717 sets fmap[p] and fmap[q] from one max_k): the owner's side
+    // computes it and publishes both endpoints' bits; the other side runs without the tally
+    phi(P, h->stream, sparse, false, 0, P.nseg_lo, 0);
+    phi(P, h->stream, sparse, true, P.nseg_lo, P.nseg, 1);
+  }
   CK(cudaGetLastError());
   return SVI_OK;
 }
@@ -769,14 +852,15 @@ int svi_ls_get_info(svi_ls *h, svi_ls_info *info) {
   info->half_edges_phi = h->he_phi;
   info->half_edges_s3 = h->he_s3;
   info->segments_phi = h->P.nseg;
-  info->segments_s3 = h->P.nseg3;
+  info->segments_s3 = h->P.nseg - h->P.nseg_lo;
   info->ld = h->P.ld;
   info->seg_len = h->seg_len;
   info->lanes = (uint32_t)(h->ops.phi_ring ? h->ops.ring_lanes : h->ops.lanes);
   info->vec = (uint32_t)(h->ops.phi_ring ? h->ops.ring_vec : h->ops.vec);
   info->ring_depth = (uint32_t)h->ops.ring_depth;
   info->device_bytes = h->device_bytes;
-  info->kernels_per_step = 7;  // phi, node, reduce, s3, reduce, lambda, refresh
+  // partition (ring tilings), phi (two launches with the tally on a whole graph), node, reduce, s3, reduce, lambda, refresh
+  info->kernels_per_step = 7 + ((h->ops.phi_ring || h->ops.s3_ring) ? 1 : 0) + (h->shard ? 0 : 1);
   return SVI_OK;
 }
 

@@ -31,13 +31,16 @@ struct Params {
   uint32_t node_begin, node_end;   // shard
   double alpha, eta0, eta1, ones_d;
   uint32_t k_div10;
-  // graph (half-edges of the shard's nodes; "upper" neighbours q>p stored last in each list)
-  const uint32_t *col;
-  const uint32_t *seg_node, *seg_beg, *seg_cnt;       // phi segments
-  uint32_t nseg;
-  const uint32_t *node_seg_off;                        // [nlocal+1] segment range of each local node
-  const uint32_t *seg3_node, *seg3_beg, *seg3_cnt;    // s3 segments (owned neighbours only)
-  uint32_t nseg3;
+  // graph: half-edges of the shard's nodes.  A node's list is [neighbours it does not own | neighbours it OWNS]
+  // (s3_owner, svi_ls.cu); each part is cut into work segments of <= seg_len neighbours.  Segment table: all "lo"
+  // segments (node order) first, [0, nseg_lo), then all "up" (owned) segments, [nseg_lo, nseg).  The phi sweep runs
+  // over all of them, the s3 sweep and the link-community tally over the "up" ones (one visit per LINK).
+  const uint32_t *col;                                 // reordered inside a segment by k_partition
+  const uint32_t *seg_node, *seg_beg, *seg_cnt;
+  uint32_t *seg_nnc;                                   // [nseg] leading not-converged neighbours of each segment
+  uint32_t nseg, nseg_lo;
+  const uint32_t *node_seg_lo, *node_seg_up;           // [nlocal+1] each: segment ranges of every local node
+  uint32_t *conv_dirty;                                // [1] some node newly converged since the last k_partition
   const double *tl;                                    // [n]
   // state
   double *b;        // [n*ld] exp(Elogpi - rowmax)   (LOGDOM: Elogpi)
@@ -112,12 +115,13 @@ __device__ __forceinline__ double digamma_pos(double x) {
 //   tally            :668-681,704-717 (COMM): arg-max community of the link
 // Output: part[seg] = sum of phi over the segment's neighbours (a K-row).
 template <int G, int V, bool LOGDOM, bool SPARSE, bool COMM>
-__global__ void __launch_bounds__(256) k_phi(const Params P) {
+__global__ void __launch_bounds__(256) k_phi(const Params P, const uint32_t seg_first, const uint32_t seg_end,
+                                             const uint32_t publish) {
   constexpr int U = (V <= 4) ? 2 : 1;   // neighbour rows in flight per group
   const unsigned mask = group_mask<G>();
   const uint32_t lane = threadIdx.x & (G - 1);
-  const uint32_t seg = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  if (seg >= P.nseg) return;
+  const uint32_t seg = seg_first + (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (seg >= seg_end) return;
   const uint32_t p = P.seg_node[seg], beg = P.seg_beg[seg], cnt = P.seg_cnt[seg];
   const uint32_t pc = P.conv[p];
   const uint32_t pa = SPARSE ? P.active[p] : 0u;
@@ -233,7 +237,10 @@ __global__ void __launch_bounds__(256) k_phi(const Params P) {
           const uint32_t ok = __shfl_xor_sync(mask, bestk, o);
           if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
         }
-        if (best > 0.0 && lane == (bestk >> 5)) mb |= 1u << (bestk & 31u);
+        if (best > 0.0 && lane == (bestk >> 5)) {
+          mb |= 1u << (bestk & 31u);
+          if (publish) atomicOr(P.mbits + (size_t)q[u] * P.words + lane, 1u << (bestk & 31u));   // one arg-max per link
+        }
       }
     }
   }
@@ -279,17 +286,21 @@ __global__ void __launch_bounds__(256) k_node(const Params P) {
   for (int j = 0; j < V; ++j) csum[j] = cs1[j] = cs2[j] = make_double2(0.0, 0.0);
 
   for (uint32_t p = P.node_begin + ggid; p < P.node_end; p += ngroups) {
-    const uint32_t s0 = P.node_seg_off[p - P.node_begin], s1 = P.node_seg_off[p - P.node_begin + 1];
     double2 acc[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[j] = make_double2(0.0, 0.0);
-    for (uint32_t s = s0; s < s1; ++s) {
-      const double *row = P.part + (size_t)s * P.ld;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {   // the node's "lo" segments, then its "up" segments: a fixed order
+      const uint32_t *off = half ? P.node_seg_up : P.node_seg_lo;
+      const uint32_t s0 = off[p - P.node_begin], s1 = off[p - P.node_begin + 1];
+      for (uint32_t s = s0; s < s1; ++s) {
+        const double *row = P.part + (size_t)s * P.ld;
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const double2 r = ld_row2(row, 2u * (lane + G * j), P.ld);
-        acc[j].x += r.x;
-        acc[j].y += r.y;
+        for (int j = 0; j < V; ++j) {
+          const double2 r = ld_row2(row, 2u * (lane + G * j), P.ld);
+          acc[j].x += r.x;
+          acc[j].y += r.y;
+        }
       }
     }
     const double tlp = P.tl[p];
@@ -357,8 +368,8 @@ __global__ void __launch_bounds__(256) k_s3(const Params P) {
 #pragma unroll
   for (int j = 0; j < V; ++j) s3[j] = make_double2(0.0, 0.0);
 
-  for (uint32_t seg = ggid; seg < P.nseg3; seg += ngroups) {
-    const uint32_t p = P.seg3_node[seg], beg = P.seg3_beg[seg], cnt = P.seg3_cnt[seg];
+  for (uint32_t seg = P.nseg_lo + ggid; seg < P.nseg; seg += ngroups) {
+    const uint32_t p = P.seg_node[seg], beg = P.seg_beg[seg], cnt = P.seg_cnt[seg];
     const uint32_t pc = P.conv[p];
     const double *mrow_p = P.mphi + (size_t)p * P.ld;
     double2 t[V];
@@ -534,7 +545,10 @@ __global__ void __launch_bounds__(256) k_refresh(const Params P) {
     total += __shfl_xor_sync(mask, total, o);
     maxk = max(maxk, __shfl_xor_sync(mask, maxk, o));
   }
-  if (total == 1u && lane == 0) P.conv[p] = maxk + 1u;   // sticky: never cleared (:472-473)
+  if (total == 1u && lane == 0) {   // sticky: never cleared (:472-473)
+    if (P.conv[p] == 0u) *P.conv_dirty = 1u;   // the neighbour lists that hold p are re-partitioned (k_partition)
+    P.conv[p] = maxk + 1u;
+  }
   if (lane == 0) P.active[p] = total;
   // active bits (only meaningful for the iter > 1000 branch; cheap enough to keep current)
   for (uint32_t w = 0; w < P.words; ++w) {

@@ -91,7 +91,7 @@ __device__ __forceinline__ uint32_t grp_of(uint32_t tid, uint32_t g) { return ti
 template <int G, int V, bool SPARSE, bool COMM>
 __device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_t lane, unsigned mask,
                                         const double2 (&be)[V], double2 (&acc)[V], uint32_t &mb, bool sparse,
-                                        uint32_t p, uint32_t q) {
+                                        uint32_t p, uint32_t q, uint32_t publish) {
   // SPARSE: restrict to the union of the endpoints' active communities (:634-664); bit e of `keep`
   // is element e = 2j + {0,1} of this lane
   uint32_t keep = 0xffffffffu;
@@ -167,7 +167,11 @@ __device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_
       const uint32_t ok = __shfl_xor_sync(mask, bestk, o);
       if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
     }
-    if (best > 0.0 && lane == (bestk >> 5)) mb |= 1u << (bestk & 31u);
+    if (best > 0.0 && lane == (bestk >> 5)) {
+      mb |= 1u << (bestk & 31u);
+      // one arg-max per link: the neighbour's bit too (a 4-byte reduction in L2; mbits is 28 MB at config 4)
+      if (publish) atomicOr(P.mbits + (size_t)q * P.words + lane, 1u << (bestk & 31u));
+    }
   }
 }
 
@@ -175,8 +179,17 @@ __device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_
 // One group per segment, 32/G segments per warp in lockstep.
 //   MODE == Phi : part[seg] = sum over the segment's neighbours of phi        (K1, src/linksampling.cc:605-725)
 //   MODE == S3  : block partials of s3[k] = sum mphi[p][k]*mphi[q][k]          (K3, :731-746)
+// Segments [seg_first, seg_end) of the segment table.  Every segment's neighbour list is PARTITIONED by
+// k_partition (below): its first seg_nnc[seg] neighbours are the not-converged ones, the rest the converged ones.
+// For a not-converged node p the full-phi links (:632-718: both or neither endpoint converged) are therefore the
+// first part and the one-hot shortcut links (:619-631) the second; for a converged p it is the other way round.
+// The ring loop runs over the full part only -- no per-neighbour flag load, no lock-stepped pass for a shortcut link
+// -- and the shortcut part is tallied G neighbours per instruction.
+//   publish (COMM only): the link-community bit is also set for the neighbour q (one arg-max per LINK, computed on
+//   the s3-owner's side only, src/linksampling.cc:704-717 sets fmap[p] and fmap[q] from one max_k)
 template <int G, int V, int R, int T, int MINB, Sweep MODE, bool SPARSE, bool COMM>
-__global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P) {
+__global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P, const uint32_t seg_first, const uint32_t seg_end,
+                                                        const uint32_t publish) {
   static_assert(R <= G && (R & (R - 1)) == 0, "ring depth: power of two, at most one chunk");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int GPB = T / G;        // groups per block
@@ -205,10 +218,7 @@ __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P) {
   __syncthreads();
 
   const double *src_rows = MODE == Sweep::Phi ? P.b : P.mphi;
-  const uint32_t nseg = MODE == Sweep::Phi ? P.nseg : P.nseg3;
-  const uint32_t *seg_node = MODE == Sweep::Phi ? P.seg_node : P.seg3_node;
-  const uint32_t *seg_beg = MODE == Sweep::Phi ? P.seg_beg : P.seg3_beg;
-  const uint32_t *seg_cnt = MODE == Sweep::Phi ? P.seg_cnt : P.seg3_cnt;
+  const uint32_t nseg = seg_end - seg_first;
 
   double2 s3acc[V];  // S3 only: per-lane column sums across this group's segments
 #pragma unroll
@@ -219,13 +229,17 @@ __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P) {
   // Phi: one segment per group (grid covers nseg).  S3: persistent, grid-stride over segments.
   const uint32_t warp_first = ggid - grp % (32 / G);   // first group id of this warp
   for (uint32_t base = warp_first; base < nseg; base += ngroups) {
-    const uint32_t seg = base + grp % (32 / G);
-    const bool have = seg < nseg;
-    const uint32_t p = have ? seg_node[seg] : 0u;
-    const uint32_t beg = have ? seg_beg[seg] : 0u;
-    const uint32_t cnt = have ? seg_cnt[seg] : 0u;
-    const uint32_t cntmax = warp_max_over_groups<G>(cnt);
+    const bool have = base + grp % (32 / G) < nseg;
+    const uint32_t seg = seg_first + base + grp % (32 / G);
+    const uint32_t p = have ? P.seg_node[seg] : 0u;
+    const uint32_t beg = have ? P.seg_beg[seg] : 0u;
+    const uint32_t cnt = have ? P.seg_cnt[seg] : 0u;
+    const uint32_t nnc = have ? P.seg_nnc[seg] : 0u;
     const uint32_t pc = have ? P.conv[p] : 0u;
+    // full-phi part [fbeg, fbeg + fcnt), shortcut part [sbeg, sbeg + scnt)
+    const uint32_t fbeg = pc ? beg + nnc : beg, fcnt = pc ? cnt - nnc : nnc;
+    const uint32_t sbeg = pc ? beg : beg + nnc, scnt = cnt - fcnt;
+    const uint32_t cntmax = warp_max_over_groups<G>(fcnt);
     uint32_t pa = 0;
     if (SPARSE) pa = have ? P.active[p] : 0u;
     const double *self_row = src_rows + (size_t)p * P.ld;
@@ -245,81 +259,81 @@ __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P) {
     double one_hot = 0.0;   // S3: shortcut mass for column pc-1
 
     // chunk 0 ids, then the ring prologue
-    uint32_t q_cur = p, qc_cur = 0, q_nxt = p, qc_nxt = 0;
-    if (lane < cnt) {
-      q_cur = __ldg(P.col + beg + lane);
-      qc_cur = P.conv[q_cur];
+    uint32_t q_cur = p, q_nxt = p;
+    if (lane < fcnt) q_cur = __ldg(P.col + fbeg + lane);
+    if (lane < R && lane < fcnt) ring.issue(lane, src_rows + (size_t)q_cur * P.ld);
+
+    // ---- shortcut links (exactly one endpoint converged), while the first rows are in flight ----
+    if (scnt) {
+      if (MODE == Sweep::Phi) {
+        // one-hot phi on the converged endpoint's community (:622-631), counted per column in shared memory
+        if (pc) {
+          if (lane == 0) hist[pc - 1u] += scnt;
+        } else {
+          for (uint32_t i = lane; i < scnt; i += G) {
+            const uint32_t qc = P.conv[__ldg(P.col + sbeg + i)];
+            if (qc) atomicAdd(hist + (qc - 1u), 1u);
+          }
+        }
+      } else if (pc) {
+        // s3[pc-1] += mphi[q][pc]  (sic, :739-740; column K reads as 0): per-lane partial sums, fixed-order merge
+        double oh = 0.0;
+        if (pc < P.k)
+          for (uint32_t i = lane; i < scnt; i += G) oh += P.mphi[(size_t)__ldg(P.col + sbeg + i) * P.ld + pc];
+        one_hot = group_sum<G>(oh, gmask);
+      } else {
+        // s3[qc-1] += mphi[p][qc]  (:741-742): the same addend for every neighbour converged to qc, so only
+        // counted here and applied once per segment
+        for (uint32_t i = lane; i < scnt; i += G) {
+          const uint32_t qc = P.conv[__ldg(P.col + sbeg + i)];
+          if (qc) atomicAdd(hist + (qc - 1u), 1u);
+        }
+      }
     }
-    if (lane < R && lane < cnt && !((pc != 0u) != (qc_cur != 0u)))
-      ring.issue(lane, src_rows + (size_t)q_cur * P.ld);
+    __syncwarp();
 
     for (uint32_t c0 = 0; c0 < cntmax; c0 += G) {
-      if (c0 > 0) {
-        q_cur = q_nxt;
-        qc_cur = qc_nxt;
-      }
-      const bool nxt_live = c0 + G + lane < cnt;
-      q_nxt = nxt_live ? __ldg(P.col + beg + c0 + G + lane) : p;
-      qc_nxt = 0;
+      if (c0 > 0) q_cur = q_nxt;
+      q_nxt = c0 + G + lane < fcnt ? __ldg(P.col + fbeg + c0 + G + lane) : p;
       const uint32_t ulim = min((uint32_t)G, cntmax - c0);
-#ifndef SVI_CONV_AT
-#define SVI_CONV_AT (G / 2)
-#endif
-      const uint32_t u_conv = min((uint32_t)(SVI_CONV_AT), ulim - 1u);
       // one copy of the body: unrolled G times with two phi_row instances each, the sweep is ~150 KB of
       // SASS and runs out of the instruction cache
 #pragma unroll 1
       for (uint32_t u = 0; u < ulim; ++u) {
         const uint32_t i = c0 + u;
-        // chunk c+1 flags: half a chunk after their ids were requested (the id load is a DRAM miss of its own;
-        // one row later its result was still in flight: 9 % of the stall samples sat on this address)
-        if (u == u_conv) qc_nxt = nxt_live ? P.conv[q_nxt] : 0u;
         // control flow is warp-uniform here: full-mask shuffles, each confined to its G-lane segment
         const uint32_t q = __shfl_sync(0xffffffffu, q_cur, u, G);
-        const uint32_t qc = __shfl_sync(0xffffffffu, qc_cur, u, G);
-        const bool live = i < cnt;
-        const bool full = live && !((pc != 0u) != (qc != 0u));
+        const bool live = i < fcnt;
         const uint32_t slot = i & (R - 1);
-        const bool allfull = __all_sync(0xffffffffu, full);
+        const bool alllive = __all_sync(0xffffffffu, live);
         const uint32_t rbase = ring.rows + slot * ring.slot_bytes;
-        if (full) ring.wait(slot);
-        if (MODE == Sweep::S3) {
-          if (full) {
+        if (live) {
+          ring.wait(slot);
+          if (MODE == Sweep::S3) {
 #pragma unroll
             for (int j = 0; j < V; ++j) {
               const double2 r = lds2(rbase + 16u * (lane + G * j));
               acc[j].x += r.x;
               acc[j].y += r.y;
             }
-          } else if (live) {
-            if (pc) {          // s3[pc-1] += mphi[q][pc]  (sic, :739-740; column K reads as 0)
-              one_hot += pc < P.k ? P.mphi[(size_t)q * P.ld + pc] : 0.0;
-            } else {           // s3[qc-1] += mphi[p][qc]  (:741-742): the same addend for every such
-              if (lane == 0) hist[qc - 1u]++;   // neighbour, so only counted here and applied once per segment
-            }
-          }
-        } else {
-          bool sparse = false;
-          if (SPARSE) sparse = full && pa < P.k_div10 && P.active[q] < P.k_div10;
-          if (full) {
-            phi_row<G, V, SPARSE, COMM>(P, rbase, lane, allfull ? 0xffffffffu : gmask, be, acc, mb, sparse, p, q);
-          } else if (live) {
-            // one-hot phi, :622-631: counted per column in shared memory (one lane, one RMW) instead of a
-            // 2V-wide compare-and-add by every lane; the counts join acc once per segment
-            if (lane == 0) hist[(pc ? pc : qc) - 1u]++;
+          } else {
+            bool sparse = false;
+            if (SPARSE) sparse = pa < P.k_div10 && P.active[q] < P.k_div10;
+            phi_row<G, V, SPARSE, COMM>(P, rbase, lane, alllive ? 0xffffffffu : gmask, be, acc, mb, sparse, p, q,
+                                        publish);
           }
         }
-        // refill this slot with neighbour i+R (its id sits in the current or the next chunk)
+        // refill this slot with neighbour i+R (its id sits in the current or the next chunk).  Ordering of the
+        // slot's reuse: every lane's generic-proxy reads of the slot (lds2 above, results consumed) precede
+        // __syncwarp; lane 0 issues the async-proxy write after it.  DESIGN.md section 4, "ring slot reuse".
         __syncwarp();
         const uint32_t ua = u + R;
         const uint32_t qa = __shfl_sync(0xffffffffu, ua < (uint32_t)G ? q_cur : q_nxt, ua & (G - 1), G);
-        const uint32_t qca = __shfl_sync(0xffffffffu, ua < (uint32_t)G ? qc_cur : qc_nxt, ua & (G - 1), G);
-        if (lane == 0 && i + R < cnt && !((pc != 0u) != (qca != 0u)))
-          ring.issue(slot, src_rows + (size_t)qa * P.ld);
+        if (lane == 0 && i + R < fcnt) ring.issue(slot, src_rows + (size_t)qa * P.ld);
       }
     }
 
-    __syncwarp();   // lane 0's tallies -> every lane
+    __syncwarp();   // the shared-memory tallies -> every lane
     if (MODE == Sweep::Phi) {
       if (have) {
         double *out = P.part + (size_t)seg * P.ld;
@@ -359,6 +373,46 @@ __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P) {
     // all rings are drained here (every issued copy was waited on), so the rows area can be reused
     block_reduce_columns<G, V>(s3acc, reinterpret_cast<double *>(smem_raw),
                                P.kpart + (size_t)blockIdx.x * CAP);
+  }
+}
+
+// Stable partition of every segment's neighbour list by the neighbours' converged flags: not-converged first,
+// seg_nnc[seg] = how many.  `converged` is sticky (src/linksampling.cc:472-473), so the lists change only in
+// sweeps where some node newly converged; *P.conv_dirty says so (set by k_refresh / svi_ls_set_converged, cleared
+// by the caller after this kernel) and lets the launch return at once otherwise.  One warp per segment, ids staged
+// in shared memory (segments hold at most kMaxSegLen neighbours), in place.
+constexpr uint32_t kMaxSegLen = 1024;
+static __global__ void __launch_bounds__(256) k_partition(const Params P, const uint32_t force) {
+  __shared__ uint32_t stage[8][kMaxSegLen];
+  if (!force && *P.conv_dirty == 0u) return;
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const uint32_t nwarps = gridDim.x * 8u;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t *col = const_cast<uint32_t *>(P.col);
+  for (uint32_t seg = blockIdx.x * 8u + w; seg < P.nseg; seg += nwarps) {
+    const uint32_t beg = P.seg_beg[seg], cnt = P.seg_cnt[seg];
+    uint32_t nnc = 0;
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 32u) {
+      const bool in = i0 + lane < cnt;
+      const uint32_t q = in ? col[beg + i0 + lane] : 0u;
+      if (in) stage[w][i0 + lane] = q;
+      nnc += __popc(__ballot_sync(0xffffffffu, in && P.conv[q] == 0u));
+    }
+    __syncwarp();
+    if (nnc != P.seg_nnc[seg] || force) {   // (a segment none of whose neighbours changed keeps its order)
+      uint32_t a = 0, b = nnc;
+      for (uint32_t i0 = 0; i0 < cnt; i0 += 32u) {
+        const bool in = i0 + lane < cnt;
+        const uint32_t q = in ? stage[w][i0 + lane] : 0u;
+        const bool nc = in && P.conv[q] == 0u;
+        const uint32_t mn = __ballot_sync(0xffffffffu, nc), mc = __ballot_sync(0xffffffffu, in && !nc);
+        if (in) col[beg + (nc ? a + __popc(mn & lt) : b + __popc(mc & lt))] = q;
+        a += __popc(mn);
+        b += __popc(mc);
+      }
+      if (lane == 0) P.seg_nnc[seg] = nnc;
+    }
+    __syncwarp();
   }
 }
 
