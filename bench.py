@@ -139,11 +139,11 @@ def heldout_pairs(n, links, count, seed=11):
 
 
 def phi_kernel_bytes(info, k):
-    """Algorithmic bytes of ONE phi-sweep launch of this implementation:
-    per half-edge one neighbour row (ld*8) + its column index (4) + its converged flag (4);
-    per segment one self row read (ld*8) + one partial row written (ld*8)."""
+    """Algorithmic bytes of ONE phi sweep of this implementation, no node converged:
+    per half-edge one neighbour row (ld*8) + its column index (4); per segment one self row read (ld*8), one
+    partial row written (ld*8) and the segment descriptor (16)."""
     ld = info["ld"]
-    return info["half_edges_phi"] * (ld * 8 + 8) + info["segments_phi"] * (2 * ld * 8 + 12)
+    return info["half_edges_phi"] * (ld * 8 + 4) + info["segments_phi"] * (2 * ld * 8 + 16)
 
 
 def step_bytes_survey(nlinks, n, k, s=8):
@@ -151,7 +151,7 @@ def step_bytes_survey(nlinks, n, k, s=8):
     return nlinks * (6 * k * s + 16) + 7 * n * k * s
 
 
-def verify_sampled_rows(step_once, get_state, get_converged, n, k, links, alpha, sample=512, seed=99):
+def verify_sampled_rows(step_once, get_state, get_converged, n, k, links, alpha, sample=512, seed=99, compute=True):
     """Parity spot-check AT THE BENCHMARKED SIZE: run one more iteration (annealing off, tally on) and recompute
     the new gamma rows of `sample` random nodes on the host in the REFERENCE's formulation -- Elogpi = psi(gamma) -
     psi(sum gamma) with scipy's digamma (independent of both the device's and the oracle's), per link the running
@@ -177,6 +177,8 @@ def verify_sampled_rows(step_once, get_state, get_converged, n, k, links, alpha,
     g1, _ = get_state()
     got = g1[pick].copy()
     del g1
+    if not compute:
+        return None
     elogpi = digamma(gr) - digamma(gr.sum(1, keepdims=True))
     elogbeta0 = digamma(lam0[:, 0]) - digamma(lam0.sum(1))
     si, di = np.searchsorted(rows, src), np.searchsorted(rows, dst)
@@ -237,7 +239,12 @@ def run_ours(args):
     t_gen = time.time() - t0
 
     stream = torch.cuda.current_stream()
+    if world > 1:
+        # the shards wait for each other's flags on their streams: a stream of its own, not the legacy default one
+        stream = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(stream)
     t0 = time.time()
+    peer, mg_ms = False, None
     if world == 1:
         eng = LinkSamplingEngine(n, k, links, device=local_rank, stream=stream.cuda_stream)
         runner = None
@@ -246,8 +253,9 @@ def run_ours(args):
     else:
         from svinet_b200.sharded import ShardedLinkSampling
         runner = ShardedLinkSampling(n, k, links, rank=rank, world=world, device=local_rank,
-                                     stream=stream.cuda_stream)
+                                     stream=stream.cuda_stream, exchange=args.exchange, chunks=args.chunks)
         eng = runner.eng
+        peer = runner.exchange == "peer"
         runner.set_state(gamma0, lam0)
         step = lambda it: runner.step(it, True, it > 0)
     info = eng.info()
@@ -263,6 +271,8 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(it); it += 1
     barrier()
+    if world > 1 and peer:
+        eng.mg_timing(True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
@@ -285,6 +295,10 @@ def run_ours(args):
     total_ms = ev[0][0].elapsed_time(ev[-1][4])
     if world == 1:
         phase_ms = [float(np.mean([ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)])) for i in range(4)]
+    elif peer:
+        mg_ms, _ = eng.mg_timing(False, read=True)
+        phase_ms = [mg_ms["wait_b_rows"] + mg_ms["phi+node"], mg_ms["allreduce_sum_s1_s2"] + mg_ms["refresh"] + mg_ms["wait_mphi_rows"],
+                    mg_ms["s3"], mg_ms["allreduce_s3+lambda"] + mg_ms["drain_own_pushes"]]
     else:
         phase_ms = runner.phase_ms(ev)
     if world > 1:
@@ -342,16 +356,52 @@ def run_ours(args):
             "what": "svi_ls_set_state(pinned host) + svi_ls_step + svi_ls_heldout + svi_ls_get_state(pinned host)"}
         del pin_g, pin_l
     else:
-        e2e = runner.e2e(step_fn=step, it0=it, steps=max(1, min(args.steps, 5)), nlinks=nlinks, unit=UNIT,
+        if peer:
+            eng.mg_share_gamma(True)     # the held-out pairs touch rows of every shard
+            runner.share_gamma = True
+        e2e_steps = max(1, min(args.steps, 10))
+        e2e = runner.e2e(step_fn=lambda i: runner.step(i, True, True), it0=it, steps=e2e_steps, nlinks=nlinks, unit=UNIT,
                          heldout=heldout_pairs(n, links, max(2, min(nlinks // 100, 2_000_000))))
+        it += e2e_steps + 1
 
     verify = None
-    if world == 1 and not args.no_verify:
+    if not args.no_verify and (world == 1 or peer):
         t0 = time.time()
-        verify = verify_sampled_rows(lambda: eng.step(it, False, True), eng.get_state,
-                                     lambda: eng.get_converged()[0], n, k, links, 1.0 / k)
-        verify["seconds"] = time.time() - t0
+        if world == 1:
+            verify = verify_sampled_rows(lambda: eng.step(it, False, True), eng.get_state,
+                                         lambda: eng.get_converged()[0], n, k, links, 1.0 / k)
+        else:
+            # collective: every rank steps; the whole gamma is on every rank (shared rows), rank 0 does the arithmetic
+            def all_step():
+                runner.step(it, False, True)
+                eng.sync()
+                dist.barrier()
+            verify = verify_sampled_rows(all_step, eng.get_state, lambda: eng.get_converged()[0], n, k, links, 1.0 / k,
+                                         compute=(rank == 0))
+        if verify is not None:
+            verify["seconds"] = time.time() - t0
         it += 1
+    checksum = None
+    if args.checksum:
+        # the same S iterations from the same start state at any GPU count: the sums agree to rounding (the per-row
+        # summation order does not depend on the sharding; the K-vector reductions do)
+        if world == 1:
+            eng.set_state(gamma0, lam0); eng.set_converged(np.zeros(n, dtype=np.uint32))
+            for i in range(args.checksum):
+                eng.step(i, True, i > 0)
+        else:
+            eng.sync(); dist.barrier()
+            runner.set_state(gamma0, lam0); eng.set_converged(np.zeros(n, dtype=np.uint32))
+            eng.sync(); dist.barrier()
+            for i in range(args.checksum):
+                runner.step(i, True, i > 0)
+            eng.sync(); dist.barrier()
+        g, lam = eng.get_state() if (world == 1 or peer) else runner.gather_state()
+        cv = eng.get_converged()[0]
+        checksum = {"steps": args.checksum, "gamma_sum": float(g.sum()), "gamma_sq_sum": float((g * g).sum()),
+                    "lambda_sum": float(lam.sum()), "converged_nodes": int((cv != 0).sum()),
+                    "converged_label_sum": int(cv.astype(np.int64).sum())}
+        del g
 
     if rank != 0:
         if world > 1:
@@ -364,7 +414,7 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: synthetic MMSB n=%d k=%d links=%d (BASELINE.json configs[3])" % (
                        args.workload, n, k, nlinks) if args.workload == "c4" else
                    "%s: synthetic MMSB n=%d k=%d links=%d" % (args.workload, n, k, nlinks),
@@ -377,13 +427,15 @@ def run_ours(args):
         "e2e": e2e,
         "gpu_launches": info["kernels_per_step"] * args.steps,
         "phase_ms": {"phi": phase_ms[0], "node": phase_ms[1], "s3": phase_ms[2], "finish": phase_ms[3]},
-        "roofline": {"bound": "hbm", "kernel": "k_phi", "achieved": phi_gbs, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_sweep_ring<Phi> (phi sweep: the two launches of a tally sweep + k_partition)"
+                     if info["ring_depth"] else "k_phi", "achieved": phi_gbs, "peak": peak, "unit": "GB/s",
                      "frac": phi_gbs / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(phi_bytes),
                      "note": "pull-form bytes of this kernel (DESIGN.md section 4)",
                      "step_gbs_survey_8d_formula": survey_gbs,
                      "step_frac_survey_8d_formula": survey_gbs / peak},
-        "verify": verify,
+        "verify": verify, "checksum": checksum,
+        "exchange": (runner.exchange if world > 1 else None), "mg_phase_ms": (mg_ms if world > 1 else None),
         "setup_s": {"generate": t_gen, "create+upload": t_create},
         "wall_s_timed_region": t_wall,
     }
@@ -538,6 +590,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true", help="(default on at 1 GPU) recompute sampled gamma rows on the host")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = svi_ls_mg_step (rows pushed over peer memory inside the library); "
+                         "nccl = torch.distributed collectives between the phases (the library baseline)")
+    ap.add_argument("--chunks", type=int, default=0, help="N > 1, peer exchange: pipeline chunks of a shard (0 = default)")
+    ap.add_argument("--checksum", type=int, default=0, metavar="S",
+                    help="also run S iterations from the start state and print sums of the resulting state")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the --impl reference arm")
     ap.add_argument("--path", default="ls", choices=["ls", "fa2"],

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SVI_LS_ABI_VERSION 1
+#define SVI_LS_ABI_VERSION 2
 
 typedef enum svi_status {
   SVI_OK = 0,
@@ -137,6 +137,46 @@ int svi_ls_phase_finish(svi_ls *h, int annealing);
  * phase_finish. */
 int svi_ls_phase_refresh(svi_ls *h, int annealing);
 int svi_ls_phase_lambda(svi_ls *h, int annealing);
+
+/* ---- multi-GPU over peer memory (the seam is still src/main.cc:337-341: one LinkSampling
+ * object, now spread over the GPUs of one box) ------------------------------------------------------------------
+ * Every shard (a handle created with its node block [node_begin, node_end) and the WHOLE link list, or at least all
+ * links incident to its block) keeps its exchange buffers in one arena.  After svi_ls_peer_attach[_local] the shards
+ * see each other's arenas (CUDA IPC between processes, peer access inside one) and svi_ls_mg_step runs the whole
+ * iteration including its exchanges: a shard pushes the rows it produced (mphi after the node pass, exp(Elogpi) /
+ * converged / active masks after the refresh) into every peer's arena with the copy engines on a side stream, beside
+ * the sweeps, and announces them with epoch-stamped flags that the consumers wait on; the K-vector all-reduces (sum,
+ * s1, s2; s3) are a push into per-source slots plus a fixed-order sum, bit-identical on every shard.  No collective
+ * library on the data path.  All shards must call svi_ls_mg_step with the same arguments, once per iteration; the
+ * call is asynchronous (svi_ls_sync reports an exchange that timed out).  Destroy the handles only after all shards
+ * have finished (the caller's barrier).
+ *   one process per GPU : svi_ls_peer_export -> exchange the blobs (e.g. torch.distributed all_gather) ->
+ *                         svi_ls_peer_attach
+ *   one process, N GPUs : svi_ls_peer_attach_local with the N handles (the C++ CLI's -gpus N)
+ *   bounds : [world+1] node blocks of all shards (bounds[rank] .. bounds[rank+1] is this handle's)
+ *   chunks : pipeline chunks of the shard's block (0 = default 4); the mphi rows of a finished chunk travel beside
+ *            the next chunk's sweep */
+size_t svi_ls_peer_blob_bytes(void);
+int svi_ls_peer_export(svi_ls *h, void *blob, size_t blob_bytes);
+int svi_ls_peer_attach(svi_ls *h, uint32_t world, uint32_t rank, const uint32_t *bounds, const void *blobs,
+                       uint32_t chunks);
+int svi_ls_peer_attach_local(svi_ls *h, uint32_t world, uint32_t rank, const uint32_t *bounds,
+                             svi_ls *const *handles, uint32_t chunks);
+int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm);
+/* also push the refreshed gamma rows, so that every shard holds the whole gamma (svi_ls_heldout on any pair,
+ * svi_ls_get_state of the whole matrix) */
+int svi_ls_mg_share_gamma(svi_ls *h, int on);
+int svi_ls_mg_error(svi_ls *h);
+/* Per-phase device times of svi_ls_mg_step, measured with events on the handle's stream: enable, run steps, then
+ * read the mean over the (at most 32) last steps into phase_ms[8]:
+ *   [0] wait for the peers' exp(Elogpi)/converged rows   (exposed exchange)
+ *   [1] partition + phi sweep + mean indicators, chunked  [2] all-reduce sum,s1,s2
+ *   [3] refresh                                           [4] wait for the peers' mphi rows (exposed exchange)
+ *   [5] s3 sweep                                          [6] all-reduce s3 + lambda
+ *   [7] wait for the own pushes to drain                  (exposed exchange) */
+int svi_ls_mg_timing(svi_ls *h, int enable, double *phase_ms, uint32_t *steps);
+/* membership words of the rows [first, first+count) only (a shard's own block) */
+int svi_ls_get_membership_rows(svi_ls *h, uint32_t first, uint32_t count, uint32_t *bits);
 
 typedef enum svi_buffer {
   SVI_BUF_EXPPI = 0,     /* double [n * ld]  exp(Elogpi - rowmax), rows padded to ld  */

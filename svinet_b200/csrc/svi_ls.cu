@@ -8,12 +8,14 @@
 #include "svi_ls_kernels.cuh"
 #include "svi_ls_ring.cuh"
 #include "svi_ls_build.cuh"
+#include "svi_ls_mg.cuh"
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 #include <new>
 #include <vector>
 
@@ -70,6 +72,7 @@ struct Ops {
 };
 
 constexpr int kThreads = 256;
+constexpr uint32_t kMaxChunks = 8;   // pipeline chunks of a shard's node block in svi_ls_mg_step
 
 template <int G, int V, bool L>
 struct Tile {
@@ -278,6 +281,27 @@ cudaError_t dalloc(T **p, size_t count, uint64_t *total) {
 
 }  // namespace
 
+// Layout of the exchange arena (identical on every shard of a run: it depends on n, ld, words only)
+struct ArenaLayout {
+  size_t b, mphi, gamma, conv[2], active, abits, mbits, kx, flags, bytes;
+  ArenaLayout() = default;
+  ArenaLayout(uint32_t n, uint32_t ld, uint32_t words) {
+    size_t at = 0;
+    auto take = [&](size_t nbytes) { const size_t o = at; at = (at + nbytes + 255) & ~(size_t)255; return o; };
+    b = take((size_t)n * ld * 8);
+    mphi = take((size_t)n * ld * 8);
+    gamma = take((size_t)n * ld * 8);
+    conv[0] = take((size_t)n * 4);
+    conv[1] = take((size_t)n * 4);
+    active = take((size_t)n * 4);
+    abits = take((size_t)n * words * 4);
+    mbits = take((size_t)n * words * 4);
+    kx = take((size_t)2 * 2 * svi::kMaxWorld * 4 * ld * 8);
+    flags = take((size_t)svi::kMaxWorld * svi::kFlagKinds * 4);
+    bytes = std::max<size_t>(at, 256);
+  }
+};
+
 struct svi_ls {
   svi_ls_config cfg{};
   int device = 0, sms = 0;
@@ -293,13 +317,34 @@ struct svi_ls {
   bool force_partition = false;
   bool shard = false;            // the handle owns a proper node block of the graph
   bool partition_every_sweep = false;   // converged flags of other shards arrive by exchange: no local dirty flag
+  // exchange arena: b, mphi, gamma, converged x2, active, active bits, membership bits, K-vector slots, flags
+  unsigned char *d_arena = nullptr;
+  ArenaLayout lay;
   double *d_tl = nullptr, *d_b = nullptr, *d_mphi = nullptr, *d_gamma = nullptr, *d_gacc = nullptr;
   double *d_part = nullptr, *d_kvec = nullptr, *d_kpart = nullptr, *d_lambda = nullptr, *d_eb = nullptr;
   double *d_scale = nullptr, *d_stage = nullptr;
-  uint32_t *d_conv = nullptr, *d_active = nullptr, *d_abits = nullptr, *d_mbits = nullptr;
-  uint32_t *d_conv_snap = nullptr;   // `converged` as the s3 sweep must see it when the refresh ran first
-  bool conv_snap_valid = false;
+  uint32_t *d_conv2[2] = {nullptr, nullptr}, *d_active = nullptr, *d_abits = nullptr, *d_mbits = nullptr;
+  int cur = 0;                   // d_conv2[cur] = `converged` as this iteration's sweeps see it
+  bool conv_pending = false;     // the refresh of this iteration has written d_conv2[cur ^ 1]; flip at its end
   size_t stage_elems = 0;
+  // segment ranges of the local nodes (host copies) and the prefix of their half-edge counts: chunk planning
+  std::vector<uint32_t> nlo, nup;
+  std::vector<uint64_t> he_prefix;
+  // ---- multi-GPU (svi_ls_peer_*, svi_ls_mg_step) ----
+  svi::Peers peers{};
+  bool mg = false, mg_ipc = false, share_gamma = false;
+  std::vector<uint32_t> bounds;          // node blocks of all shards
+  std::vector<uint32_t> chunk_nodes;     // the own block cut into pipeline chunks: chunk c = [chunk_nodes[c], chunk_nodes[c+1])
+  cudaStream_t side = nullptr, own_main = nullptr;
+  cudaEvent_t ev_chunk = nullptr, ev_refresh = nullptr, ev_side = nullptr;
+  uint32_t epoch = 0, gamma_epoch = 0;
+  uint32_t *d_mg_err = nullptr;
+  // optional per-phase timing of svi_ls_mg_step (svi_ls_mg_timing): events on the main stream, ring of steps
+  static constexpr int kTimedSteps = 32, kMarks = 9;
+  bool timing = false;
+  cudaEvent_t tev[kTimedSteps][kMarks] = {};
+  uint32_t tsteps = 0;
+  uint64_t mg_timeout_ns = 20ull * 1000000000ull;
 };
 
 namespace {
@@ -318,12 +363,22 @@ struct DeviceGuard {
 };
 
 void free_all(svi_ls *h) {
+  if (h->mg_ipc)
+    for (uint32_t r = 0; r < h->peers.world; ++r)
+      if (r != h->peers.rank && h->peers.arena[r]) cudaIpcCloseMemHandle(h->peers.arena[r]);
   void *ptrs[] = {h->d_col, h->d_seg_node, h->d_seg_beg, h->d_seg_cnt, h->d_seg_nnc, h->d_node_seg_lo,
-                  h->d_node_seg_up, h->d_conv_dirty, h->d_tl, h->d_b, h->d_mphi, h->d_gamma, h->d_gacc, h->d_part,
-                  h->d_kvec, h->d_kpart, h->d_lambda, h->d_eb, h->d_scale, h->d_stage, h->d_conv, h->d_active,
-                  h->d_abits, h->d_mbits, h->d_conv_snap};
+                  h->d_node_seg_up, h->d_conv_dirty, h->d_tl, h->d_arena, h->d_gacc, h->d_part,
+                  h->d_kvec, h->d_kpart, h->d_lambda, h->d_eb, h->d_scale, h->d_stage, h->d_mg_err};
   for (void *p : ptrs)
     if (p) cudaFree(p);
+  for (auto &row : h->tev)
+    for (cudaEvent_t ev : row)
+      if (ev) cudaEventDestroy(ev);
+  if (h->ev_chunk) cudaEventDestroy(h->ev_chunk);
+  if (h->ev_refresh) cudaEventDestroy(h->ev_refresh);
+  if (h->ev_side) cudaEventDestroy(h->ev_side);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->own_main) cudaStreamDestroy(h->own_main);
 }
 
 int ensure_stage(svi_ls *h, size_t elems) {
@@ -355,6 +410,9 @@ inline void push_segments(uint32_t node, uint32_t beg, uint32_t deg, uint32_t se
 }  // namespace
 
 extern "C" {
+
+static void mg_await_rows(svi_ls *h);
+int svi_ls_mg_error(svi_ls *h);
 
 const char *svi_ls_last_error(void) { return g_err; }
 int svi_ls_abi_version(void) { return SVI_LS_ABI_VERSION; }
@@ -543,20 +601,26 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   A(dalloc(&h->d_node_seg_up, nlocal + 1, &tot));
   A(dalloc(&h->d_conv_dirty, 1, &tot));
   A(dalloc(&h->d_tl, n, &tot));
-  A(dalloc(&h->d_b, nld, &tot));
-  A(dalloc(&h->d_mphi, nld, &tot));
-  A(dalloc(&h->d_gamma, nld, &tot));
+  h->lay = ArenaLayout(n, ld, words);
+  A(dalloc(&h->d_arena, h->lay.bytes, &tot));
+  if (e == cudaSuccess) {
+    h->d_b = reinterpret_cast<double *>(h->d_arena + h->lay.b);
+    h->d_mphi = reinterpret_cast<double *>(h->d_arena + h->lay.mphi);
+    h->d_gamma = reinterpret_cast<double *>(h->d_arena + h->lay.gamma);
+    h->d_conv2[0] = reinterpret_cast<uint32_t *>(h->d_arena + h->lay.conv[0]);
+    h->d_conv2[1] = reinterpret_cast<uint32_t *>(h->d_arena + h->lay.conv[1]);
+    h->d_active = reinterpret_cast<uint32_t *>(h->d_arena + h->lay.active);
+    h->d_abits = reinterpret_cast<uint32_t *>(h->d_arena + h->lay.abits);
+    h->d_mbits = reinterpret_cast<uint32_t *>(h->d_arena + h->lay.mbits);
+  }
+  A(dalloc(&h->d_mg_err, 1, &tot));
   A(dalloc(&h->d_gacc, nld, &tot));
   A(dalloc(&h->d_part, (size_t)nseg * ld, &tot));
   A(dalloc(&h->d_kvec, 4 * (size_t)ld, &tot));
-  A(dalloc(&h->d_kpart, (size_t)h->kpart_blocks * 3 * cap, &tot));
+  A(dalloc(&h->d_kpart, (size_t)std::max<size_t>(h->kpart_blocks, (size_t)kMaxChunks * h->blocks_node) * 3 * cap, &tot));
   A(dalloc(&h->d_lambda, 2 * (size_t)k, &tot));
   A(dalloc(&h->d_eb, ld, &tot));
   A(dalloc(&h->d_scale, ld, &tot));
-  A(dalloc(&h->d_conv, n, &tot));
-  A(dalloc(&h->d_active, n, &tot));
-  A(dalloc(&h->d_abits, (size_t)n * words, &tot));
-  A(dalloc(&h->d_mbits, (size_t)n * words, &tot));
   auto H2D = [&](void *d, const void *s, size_t bytes) {
     if (bytes) A(cudaMemcpy(d, s, bytes, cudaMemcpyHostToDevice));
   };
@@ -579,7 +643,7 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
 
   Params &P = h->P;
   P.n = n; P.k = k; P.ld = ld; P.words = words;
-  P.node_begin = nb; P.node_end = ne;
+  P.node_begin = nb; P.node_end = ne; P.shard_begin = nb;
   P.alpha = cfg->alpha; P.eta0 = cfg->eta0; P.eta1 = cfg->eta1; P.ones_d = (double)cfg->ones;
   P.k_div10 = k / 10;
   P.col = h->d_col;
@@ -590,7 +654,11 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   P.tl = h->d_tl;
   P.b = h->d_b; P.mphi = h->d_mphi; P.gamma = h->d_gamma; P.gacc = h->d_gacc; P.part = h->d_part;
   P.kvec = h->d_kvec; P.kpart = h->d_kpart; P.lambda = h->d_lambda; P.eb = h->d_eb; P.scale = h->d_scale;
-  P.conv = h->d_conv; P.active = h->d_active; P.abits = h->d_abits; P.mbits = h->d_mbits;
+  P.conv = h->d_conv2[0]; P.conv_next = h->d_conv2[1]; P.active = h->d_active; P.abits = h->d_abits; P.mbits = h->d_mbits;
+  h->nlo = std::move(nlo);
+  h->nup = std::move(nup);
+  h->he_prefix.assign(nlocal + 1, 0);
+  for (uint32_t v = 0; v < nlocal; ++v) h->he_prefix[v + 1] = h->he_prefix[v] + deg_lo[v] + deg_up[v];
   *out = h;
   return SVI_OK;
 }
@@ -599,6 +667,7 @@ void svi_ls_destroy(svi_ls *h) {
   if (!h) return;
   DeviceGuard guard(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->side) cudaStreamSynchronize(h->side);
   free_all(h);
   delete h;
 }
@@ -613,6 +682,8 @@ int svi_ls_sync(svi_ls *h) {
   if (!h) return fail(SVI_ERR_INVALID, "null handle");
   DeviceGuard guard(h->device);
   CK(cudaStreamSynchronize(h->stream));
+  if (h->side) CK(cudaStreamSynchronize(h->side));
+  if (h->mg) return svi_ls_mg_error(h);
   return SVI_OK;
 }
 
@@ -621,6 +692,7 @@ int svi_ls_set_state(svi_ls *h, const double *gamma, const double *lambda) {
   DeviceGuard guard(h->device);
   const Params &P = h->P;
   const size_t nk = (size_t)P.n * P.k;
+  mg_await_rows(h);   // (rows the peers pushed for the abandoned state must not land on top of the new one)
   if (P.ld == P.k) {
     CK(cudaMemcpyAsync(h->d_gamma, gamma, nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   } else {
@@ -646,6 +718,7 @@ int svi_ls_get_state(svi_ls *h, double *gamma, double *lambda) {
   DeviceGuard guard(h->device);
   const Params &P = h->P;
   const size_t nk = (size_t)P.n * P.k;
+  if (gamma && h->share_gamma) mg_await_rows(h);   // the other shards' rows of the last iteration
   if (gamma) {
     if (P.ld == P.k) {
       CK(cudaMemcpyAsync(gamma, h->d_gamma, nk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -665,7 +738,7 @@ int svi_ls_get_state(svi_ls *h, double *gamma, double *lambda) {
 int svi_ls_set_converged(svi_ls *h, const uint32_t *converged) {
   if (!h || !converged) return fail(SVI_ERR_INVALID, "svi_ls_set_converged: null argument");
   DeviceGuard guard(h->device);
-  CK(cudaMemcpyAsync(h->d_conv, converged, (size_t)h->P.n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_conv2[h->cur], converged, (size_t)h->P.n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->force_partition = true;   // arbitrary flags (a resume may even clear some): rebuild every segment's partition
   return SVI_OK;
@@ -674,8 +747,9 @@ int svi_ls_set_converged(svi_ls *h, const uint32_t *converged) {
 int svi_ls_get_converged(svi_ls *h, uint32_t *converged, uint32_t *active_comms) {
   if (!h) return fail(SVI_ERR_INVALID, "null handle");
   DeviceGuard guard(h->device);
+  mg_await_rows(h);   // sharded: the other shards' flags of the last iteration
   if (converged)
-    CK(cudaMemcpyAsync(converged, h->d_conv, (size_t)h->P.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(converged, h->d_conv2[h->cur], (size_t)h->P.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   if (active_comms)
     CK(cudaMemcpyAsync(active_comms, h->d_active, (size_t)h->P.n * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                        h->stream));
@@ -683,34 +757,88 @@ int svi_ls_get_converged(svi_ls *h, uint32_t *converged, uint32_t *active_comms)
   return SVI_OK;
 }
 
-int svi_ls_phase_phi(svi_ls *h, uint32_t iter, int write_comm) {
-  if (!h) return fail(SVI_ERR_INVALID, "null handle");
-  DeviceGuard guard(h->device);
+}  // extern "C"
+
+namespace {
+
+void flip_converged(svi_ls *h) {
+  h->cur ^= 1;
+  h->P.conv = h->d_conv2[h->cur];
+  h->P.conv_next = h->d_conv2[h->cur ^ 1];
+  h->conv_pending = false;
+}
+
+// start of an iteration: re-partition the neighbour lists if nodes converged, clear the link-community bits
+int begin_iteration(svi_ls *h, cudaStream_t st, int write_comm) {
   const Params &P = h->P;
-  h->conv_snap_valid = false;   // a new iteration: a snapshot left by an unfinished refresh/lambda pair is stale
+  if (h->conv_pending) flip_converged(h);   // (an iteration abandoned between its refresh and its lambda phase)
   // the ring sweeps read neighbour lists partitioned by the converged flags (svi_ls_ring.cuh: k_partition); nodes
   // converge in k_refresh, at the end of the previous iteration
   if ((h->ops.phi_ring || h->ops.s3_ring) && P.nseg) {
     const bool force = h->force_partition || h->partition_every_sweep;
-    svi::k_partition<<<(uint32_t)std::min<uint64_t>((P.nseg + 7) / 8, (uint64_t)h->sms * 8), 256, 0, h->stream>>>(P, force);
-    CK(cudaMemsetAsync(h->d_conv_dirty, 0, sizeof(uint32_t), h->stream));
+    svi::k_partition<<<(uint32_t)std::min<uint64_t>((P.nseg + 7) / 8, (uint64_t)h->sms * 8), 256, 0, st>>>(h->P, force);
+    CK(cudaMemsetAsync(h->d_conv_dirty, 0, sizeof(uint32_t), st));
     h->force_partition = false;
   }
   if (write_comm)  // _communities.clear(); _fmap.zero()  (src/linksampling.cc:584-587)
-    CK(cudaMemsetAsync(h->d_mbits, 0, (size_t)P.n * P.words * sizeof(uint32_t), h->stream));
+    CK(cudaMemsetAsync(h->d_mbits, 0, (size_t)P.n * P.words * sizeof(uint32_t), st));
+  return SVI_OK;
+}
+
+// phi sweep over the "lo" segments [lo0, lo1) and the "up" segments [up0, up1)
+void launch_phi(svi_ls *h, cudaStream_t st, uint32_t iter, int write_comm, uint32_t lo0, uint32_t lo1, uint32_t up0,
+                uint32_t up1) {
+  const Params &P = h->P;
   auto phi = h->ops.phi_ring ? h->ops.phi_ring : h->ops.phi;
   const bool sparse = iter > 1000 && P.k_div10 > 0;
+  const bool whole = lo0 == 0 && lo1 == P.nseg_lo && up0 == P.nseg_lo && up1 == P.nseg;
   if (!write_comm) {
-    phi(P, h->stream, sparse, false, 0, P.nseg, 0);
+    if (whole) phi(P, st, sparse, false, 0, P.nseg, 0);
+    else { phi(P, st, sparse, false, lo0, lo1, 0); phi(P, st, sparse, false, up0, up1, 0); }
   } else if (h->shard) {
     // a shard holds the membership words of its own nodes only: the arg-max is taken on both sides of a link
-    phi(P, h->stream, sparse, true, 0, P.nseg, 0);
+    if (whole) phi(P, st, sparse, true, 0, P.nseg, 0);
+    else { phi(P, st, sparse, true, lo0, lo1, 0); phi(P, st, sparse, true, up0, up1, 0); }
   } else {
     // one arg-max per LINK (src/linksampling.cc:704-717 sets fmap[p] and fmap[q] from one max_k): the owner's side
     // computes it and publishes both endpoints' bits; the other side runs without the tally
-    phi(P, h->stream, sparse, false, 0, P.nseg_lo, 0);
-    phi(P, h->stream, sparse, true, P.nseg_lo, P.nseg, 1);
+    phi(P, st, sparse, false, lo0, lo1, 0);
+    phi(P, st, sparse, true, up0, up1, 1);
   }
+}
+
+// mean indicators of the nodes [v0, v1) -> block partials of chunk slot `c`
+void launch_node(svi_ls *h, cudaStream_t st, uint32_t v0, uint32_t v1, uint32_t c) {
+  Params P = h->P;
+  P.node_begin = v0;
+  P.node_end = v1;
+  P.kpart = h->d_kpart + (size_t)c * h->blocks_node * 3 * (2 * h->ops.lanes * h->ops.vec);
+  h->ops.node(P, st, h->blocks_node);
+}
+
+void launch_s3(svi_ls *h, cudaStream_t st) {
+  const Params &P = h->P;
+  uint32_t cap3 = 2 * h->ops.lanes * h->ops.vec;
+  if (h->ops.s3_ring) {
+    h->ops.s3_ring(P, st, h->blocks_s3);
+    cap3 = 2 * h->ops.s3_lanes * h->ops.s3_vec;
+  } else {
+    h->ops.s3(P, st, h->blocks_s3);
+  }
+  svi::k_reduce_kpart<<<2, 256, 0, st>>>(h->d_kpart, h->blocks_s3, 1, cap3, h->d_kvec + 3 * (size_t)P.ld, P.ld);
+}
+
+}  // namespace
+
+extern "C" {
+
+int svi_ls_phase_phi(svi_ls *h, uint32_t iter, int write_comm) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  const Params &P = h->P;
+  int rc = begin_iteration(h, h->stream, write_comm);
+  if (rc) return rc;
+  launch_phi(h, h->stream, iter, write_comm, 0, P.nseg_lo, P.nseg_lo, P.nseg);
   CK(cudaGetLastError());
   return SVI_OK;
 }
@@ -719,7 +847,7 @@ int svi_ls_phase_node(svi_ls *h) {
   if (!h) return fail(SVI_ERR_INVALID, "null handle");
   DeviceGuard guard(h->device);
   const Params &P = h->P;
-  h->ops.node(P, h->stream, h->blocks_node);
+  launch_node(h, h->stream, P.node_begin, P.node_end, 0);
   svi::k_reduce_kpart<<<4, 256, 0, h->stream>>>(h->d_kpart, h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec,
                                                h->d_kvec, P.ld);
   CK(cudaGetLastError());
@@ -729,16 +857,9 @@ int svi_ls_phase_node(svi_ls *h) {
 int svi_ls_phase_s3(svi_ls *h) {
   if (!h) return fail(SVI_ERR_INVALID, "null handle");
   DeviceGuard guard(h->device);
-  Params P = h->P;
-  if (h->conv_snap_valid) P.conv = h->d_conv_snap;   // the reference's s3 loop (:731-746) runs BEFORE prune (:761)
-  uint32_t cap3 = 2 * h->ops.lanes * h->ops.vec;
-  if (h->ops.s3_ring) {
-    h->ops.s3_ring(P, h->stream, h->blocks_s3);
-    cap3 = 2 * h->ops.s3_lanes * h->ops.s3_vec;
-  } else {
-    h->ops.s3(P, h->stream, h->blocks_s3);
-  }
-  svi::k_reduce_kpart<<<2, 256, 0, h->stream>>>(h->d_kpart, h->blocks_s3, 1, cap3, h->d_kvec + 3 * (size_t)P.ld, P.ld);
+  // reads h->P.conv, the flags of the START of this iteration even when the refresh already ran: the reference's
+  // s3 loop (:731-746) precedes prune (:761), whose result lives in P.conv_next until the iteration ends
+  launch_s3(h, h->stream);
   CK(cudaGetLastError());
   return SVI_OK;
 }
@@ -749,17 +870,16 @@ int svi_ls_phase_finish(svi_ls *h, int annealing) {
   h->ops.lambda(h->P, h->stream, annealing, 1);
   h->ops.refresh(h->P, h->stream, true);
   CK(cudaGetLastError());
+  flip_converged(h);
   return SVI_OK;
 }
 
 int svi_ls_phase_refresh(svi_ls *h, int annealing) {
   if (!h) return fail(SVI_ERR_INVALID, "null handle");
   DeviceGuard guard(h->device);
-  if (!h->d_conv_snap) CK(cudaMalloc((void **)&h->d_conv_snap, std::max<size_t>(h->P.n, 1) * sizeof(uint32_t)));
-  CK(cudaMemcpyAsync(h->d_conv_snap, h->d_conv, (size_t)h->P.n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
-  h->conv_snap_valid = true;
   svi::k_scale<<<1, 256, 0, h->stream>>>(h->P, annealing);
   h->ops.refresh(h->P, h->stream, true);
+  h->conv_pending = true;
   CK(cudaGetLastError());
   return SVI_OK;
 }
@@ -768,7 +888,7 @@ int svi_ls_phase_lambda(svi_ls *h, int annealing) {
   if (!h) return fail(SVI_ERR_INVALID, "null handle");
   DeviceGuard guard(h->device);
   h->ops.lambda(h->P, h->stream, annealing, 1);
-  h->conv_snap_valid = false;
+  if (h->conv_pending) flip_converged(h);
   CK(cudaGetLastError());
   return SVI_OK;
 }
@@ -779,6 +899,263 @@ int svi_ls_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
   if ((rc = svi_ls_phase_node(h))) return rc;
   if ((rc = svi_ls_phase_s3(h))) return rc;
   return svi_ls_phase_finish(h, annealing);
+}
+
+// ---- multi-GPU over peer memory (svi_ls_mg.cuh) ------------------------------------------------------------------
+
+struct svi_ls_peer_blob_layout {
+  uint64_t magic;
+  uint32_t n, ld, words, device;
+  uint64_t arena_bytes, pid;
+  cudaIpcMemHandle_t mem;
+};
+static const uint64_t kBlobMagic = 0x5356494c53424c32ull;
+
+size_t svi_ls_peer_blob_bytes(void) { return sizeof(svi_ls_peer_blob_layout); }
+
+int svi_ls_peer_export(svi_ls *h, void *blob, size_t blob_bytes) {
+  if (!h || !blob || blob_bytes < sizeof(svi_ls_peer_blob_layout)) return fail(SVI_ERR_INVALID, "svi_ls_peer_export: bad argument");
+  DeviceGuard guard(h->device);
+  svi_ls_peer_blob_layout b;
+  memset(&b, 0, sizeof b);
+  b.magic = kBlobMagic;
+  b.n = h->P.n; b.ld = h->P.ld; b.words = h->P.words; b.device = (uint32_t)h->device;
+  b.arena_bytes = h->lay.bytes;
+  b.pid = (uint64_t)getpid();
+  CK(cudaIpcGetMemHandle(&b.mem, h->d_arena));
+  memcpy(blob, &b, sizeof b);
+  return SVI_OK;
+}
+
+static int mg_finish_attach(svi_ls *h, uint32_t world, uint32_t rank, const uint32_t *bounds, uint32_t chunks) {
+  if (bounds[0] != 0 || bounds[world] != h->P.n || bounds[rank] != h->P.node_begin || bounds[rank + 1] != h->P.node_end)
+    return fail(SVI_ERR_INVALID, "svi_ls_peer_attach: bounds do not match the handle's node block [%u,%u)", h->P.node_begin,
+                h->P.node_end);
+  h->bounds.assign(bounds, bounds + world + 1);
+  h->peers.world = world;
+  h->peers.rank = rank;
+  h->peers.arena[rank] = h->d_arena;
+  h->peers.flags_off = h->lay.flags;
+  h->peers.kx_off = h->lay.kx;
+  h->peers.kx_stride = 4 * h->P.ld;
+  if (!h->stream) {   // the legacy default stream would serialise the shards of one process: own streams
+    CK(cudaStreamCreateWithFlags(&h->own_main, cudaStreamNonBlocking));
+    h->stream = h->own_main;
+  }
+  if (!h->side) CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  if (!h->ev_chunk) CK(cudaEventCreateWithFlags(&h->ev_chunk, cudaEventDisableTiming));
+  if (!h->ev_refresh) CK(cudaEventCreateWithFlags(&h->ev_refresh, cudaEventDisableTiming));
+  if (!h->ev_side) CK(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
+  // pipeline chunks of the own block, balanced by half-edges
+  const char *ce = getenv("SVI_LS_MG_CHUNKS");
+  uint32_t c = chunks ? chunks : (ce ? (uint32_t)atoi(ce) : 4u);
+  c = std::max(1u, std::min(c, kMaxChunks));
+  if (world == 1) c = 1;
+  h->chunk_nodes.assign(1, h->P.node_begin);
+  const uint64_t total = h->he_prefix[h->nlocal];
+  for (uint32_t i = 1; i < c; ++i) {
+    const uint64_t target = total * i / c;
+    uint32_t v = (uint32_t)(std::lower_bound(h->he_prefix.begin(), h->he_prefix.end(), target) - h->he_prefix.begin());
+    v = std::min(v, h->nlocal);
+    h->chunk_nodes.push_back(std::max(h->chunk_nodes.back(), h->P.node_begin + v));
+  }
+  h->chunk_nodes.push_back(h->P.node_end);
+  h->epoch = 0;
+  h->mg = true;
+  h->partition_every_sweep = world > 1;
+  const char *te = getenv("SVI_LS_MG_TIMEOUT_S");
+  if (te && atof(te) > 0) h->mg_timeout_ns = (uint64_t)(atof(te) * 1e9);
+  return SVI_OK;
+}
+
+int svi_ls_peer_attach(svi_ls *h, uint32_t world, uint32_t rank, const uint32_t *bounds, const void *blobs,
+                       uint32_t chunks) {
+  if (!h || !bounds || !blobs || world < 1 || world > svi::kMaxWorld || rank >= world)
+    return fail(SVI_ERR_INVALID, "svi_ls_peer_attach: bad argument (world <= %u)", svi::kMaxWorld);
+  if (h->mg) return fail(SVI_ERR_INVALID, "svi_ls_peer_attach: already attached");
+  DeviceGuard guard(h->device);
+  const svi_ls_peer_blob_layout *bl = reinterpret_cast<const svi_ls_peer_blob_layout *>(blobs);
+  for (uint32_t r = 0; r < world; ++r) {
+    if (bl[r].magic != kBlobMagic || bl[r].n != h->P.n || bl[r].ld != h->P.ld || bl[r].arena_bytes != h->lay.bytes)
+      return fail(SVI_ERR_INVALID, "svi_ls_peer_attach: blob %u does not describe a shard of this problem", r);
+    if (r == rank) continue;
+    if (bl[r].pid == (uint64_t)getpid())
+      return fail(SVI_ERR_INVALID, "svi_ls_peer_attach: shard %u lives in this process; use svi_ls_peer_attach_local", r);
+    void *ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, bl[r].mem, cudaIpcMemLazyEnablePeerAccess));
+    h->peers.arena[r] = static_cast<unsigned char *>(ptr);
+  }
+  h->mg_ipc = true;
+  return mg_finish_attach(h, world, rank, bounds, chunks);
+}
+
+int svi_ls_peer_attach_local(svi_ls *h, uint32_t world, uint32_t rank, const uint32_t *bounds, svi_ls *const *handles,
+                             uint32_t chunks) {
+  if (!h || !bounds || !handles || world < 1 || world > svi::kMaxWorld || rank >= world || handles[rank] != h)
+    return fail(SVI_ERR_INVALID, "svi_ls_peer_attach_local: bad argument (world <= %u)", svi::kMaxWorld);
+  if (h->mg) return fail(SVI_ERR_INVALID, "svi_ls_peer_attach_local: already attached");
+  DeviceGuard guard(h->device);
+  for (uint32_t r = 0; r < world; ++r) {
+    const svi_ls *o = handles[r];
+    if (!o || o->P.n != h->P.n || o->P.ld != h->P.ld || o->lay.bytes != h->lay.bytes)
+      return fail(SVI_ERR_INVALID, "svi_ls_peer_attach_local: handle %u is not a shard of this problem", r);
+    if (o->device != h->device) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, h->device, o->device));
+      if (!can) return fail(SVI_ERR_UNSUPPORTED, "svi_ls_peer_attach_local: device %d cannot access device %d", h->device, o->device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(SVI_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", o->device, cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    h->peers.arena[r] = o->d_arena;
+  }
+  return mg_finish_attach(h, world, rank, bounds, chunks);
+}
+
+int svi_ls_mg_share_gamma(svi_ls *h, int on) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  h->share_gamma = on != 0;
+  return SVI_OK;
+}
+
+// copy rows [v0, v1) of an arena matrix (row = `row_bytes` bytes at arena offset `off`) into every peer's arena
+static int mg_push_rows(svi_ls *h, cudaStream_t st, size_t off, size_t row_bytes, uint32_t v0, uint32_t v1) {
+  if (v1 <= v0) return SVI_OK;
+  const size_t at = off + (size_t)v0 * row_bytes, bytes = (size_t)(v1 - v0) * row_bytes;
+  for (uint32_t d = 1; d < h->peers.world; ++d) {
+    const uint32_t r = (h->peers.rank + d) % h->peers.world;
+    CK(cudaMemcpyAsync(h->peers.arena[r] + at, h->d_arena + at, bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  return SVI_OK;
+}
+
+int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  if (!h->mg) return fail(SVI_ERR_INVALID, "svi_ls_mg_step: svi_ls_peer_attach[_local] first");
+  DeviceGuard guard(h->device);
+  const svi::Peers &pr = h->peers;
+  cudaStream_t mn = h->stream, side = h->side;
+  const Params &P = h->P;
+  const uint32_t e = ++h->epoch, par = e & 1u, ld = P.ld;
+  const bool multi = pr.world > 1;
+  int rc;
+  cudaEvent_t *tev = h->timing ? h->tev[h->tsteps++ % svi_ls::kTimedSteps] : nullptr;
+  auto mark = [&](int i) { if (tev) cudaEventRecord(tev[i], mn); };
+  mark(0);
+  // the peers' rows for this iteration (b, converged, ...) were pushed during their previous refresh
+  if (multi && e > 1) svi::k_mg_wait<<<1, 32, 0, mn>>>(pr, svi::FLAG_B, e - 1, h->d_mg_err, h->mg_timeout_ns);
+  mark(1);
+  if ((rc = begin_iteration(h, mn, write_comm))) return rc;
+  // phi sweep + mean indicators chunk by chunk; the finished chunk's mphi rows travel to the peers (side stream,
+  // copy engines) beside the next chunk's sweep
+  const uint32_t nchunks = (uint32_t)h->chunk_nodes.size() - 1, nb = P.node_begin;
+  for (uint32_t c = 0; c < nchunks; ++c) {
+    const uint32_t v0 = h->chunk_nodes[c], v1 = h->chunk_nodes[c + 1];
+    launch_phi(h, mn, iter, write_comm, h->nlo[v0 - nb], h->nlo[v1 - nb], h->nup[v0 - nb], h->nup[v1 - nb]);
+    launch_node(h, mn, v0, v1, c);
+    if (multi) {
+      CK(cudaEventRecord(h->ev_chunk, mn));
+      CK(cudaStreamWaitEvent(side, h->ev_chunk, 0));
+      if ((rc = mg_push_rows(h, side, h->lay.mphi, (size_t)ld * 8, v0, v1))) return rc;
+    }
+  }
+  if (multi) svi::k_mg_signal<<<1, 32, 0, side>>>(pr, svi::FLAG_M, e);
+  mark(2);
+  svi::k_reduce_kpart<<<4, 256, 0, mn>>>(h->d_kpart, nchunks * h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec, h->d_kvec, ld);
+  if (multi) {   // all-reduce of sum, s1, s2 (`sum` feeds the annealing rescale, :541-542)
+    svi::k_mg_kx_push<<<1, 256, 0, mn>>>(pr, h->d_kvec, 3 * ld, par, 0, svi::FLAG_KXN, e);
+    svi::k_mg_kx_sum<<<1, 256, 0, mn>>>(pr, h->d_kvec, 3 * ld, par, 0, svi::FLAG_KXN, e, h->d_mg_err, h->mg_timeout_ns);
+  }
+  mark(3);
+  // refresh BEFORE the s3 sweep (it needs `sum` only); its rows travel beside the sweep
+  svi::k_scale<<<1, 256, 0, mn>>>(P, annealing);
+  h->ops.refresh(P, mn, true);
+  h->conv_pending = true;
+  mark(4);
+  if (multi) {
+    CK(cudaEventRecord(h->ev_refresh, mn));
+    CK(cudaStreamWaitEvent(side, h->ev_refresh, 0));
+    const uint32_t v0 = P.node_begin, v1 = P.node_end;
+    if ((rc = mg_push_rows(h, side, h->lay.b, (size_t)ld * 8, v0, v1))) return rc;
+    if ((rc = mg_push_rows(h, side, h->lay.conv[h->cur ^ 1], 4, v0, v1))) return rc;
+    if (iter >= 1000) {   // the active-set branch (iter > 1000, :634) reads the neighbours' counts and masks
+      if ((rc = mg_push_rows(h, side, h->lay.active, 4, v0, v1))) return rc;
+      if ((rc = mg_push_rows(h, side, h->lay.abits, (size_t)P.words * 4, v0, v1))) return rc;
+    }
+    if (h->share_gamma && (rc = mg_push_rows(h, side, h->lay.gamma, (size_t)ld * 8, v0, v1))) return rc;
+    svi::k_mg_signal<<<1, 32, 0, side>>>(pr, svi::FLAG_B, e);
+    svi::k_mg_wait<<<1, 32, 0, mn>>>(pr, svi::FLAG_M, e, h->d_mg_err, h->mg_timeout_ns);
+  }
+  mark(5);
+  launch_s3(h, mn);
+  mark(6);
+  if (multi) {
+    svi::k_mg_kx_push<<<1, 256, 0, mn>>>(pr, h->d_kvec + 3 * (size_t)ld, ld, par, 1, svi::FLAG_KXS, e);
+    svi::k_mg_kx_sum<<<1, 256, 0, mn>>>(pr, h->d_kvec + 3 * (size_t)ld, ld, par, 1, svi::FLAG_KXS, e, h->d_mg_err,
+                                       h->mg_timeout_ns);
+  }
+  h->ops.lambda(P, mn, annealing, 1);
+  flip_converged(h);
+  mark(7);
+  if (multi) {   // our own pushes belong to the iteration (the peers' are awaited when they are needed)
+    CK(cudaEventRecord(h->ev_side, side));
+    CK(cudaStreamWaitEvent(mn, h->ev_side, 0));
+  }
+  mark(8);
+  CK(cudaGetLastError());
+  return SVI_OK;
+}
+
+int svi_ls_mg_timing(svi_ls *h, int enable, double *phase_ms, uint32_t *steps) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  if (phase_ms) {   // mean over the recorded steps (at most the last kTimedSteps), then reset
+    CK(cudaStreamSynchronize(h->stream));
+    const uint32_t cnt = std::min<uint32_t>(h->tsteps, svi_ls::kTimedSteps);
+    for (int i = 0; i < svi_ls::kMarks - 1; ++i) phase_ms[i] = 0.0;
+    for (uint32_t s = 0; s < cnt; ++s)
+      for (int i = 0; i < svi_ls::kMarks - 1; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->tev[s][i], h->tev[s][i + 1]));
+        phase_ms[i] += ms / cnt;
+      }
+    if (steps) *steps = cnt;
+    h->tsteps = 0;
+  }
+  if (enable && !h->tev[0][0])
+    for (auto &row : h->tev)
+      for (cudaEvent_t &ev : row) CK(cudaEventCreate(&ev));
+  h->timing = enable != 0;
+  h->tsteps = 0;
+  return SVI_OK;
+}
+
+// rows of the peers that the last svi_ls_mg_step's refresh pushed (gamma when shared, b, converged) are complete
+// on return of the stream work queued here
+static void mg_await_rows(svi_ls *h) {
+  if (h->mg && h->peers.world > 1 && h->epoch > 0)
+    svi::k_mg_wait<<<1, 32, 0, h->stream>>>(h->peers, svi::FLAG_B, h->epoch, h->d_mg_err, h->mg_timeout_ns);
+}
+
+int svi_ls_mg_error(svi_ls *h) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  uint32_t v = 0;
+  CK(cudaMemcpy(&v, h->d_mg_err, sizeof v, cudaMemcpyDeviceToHost));
+  if (v) return fail(SVI_ERR_CUDA, "multi-GPU exchange timed out: flag kind %u from shard %u never arrived", (v >> 4) & 15u, v & 15u);
+  return SVI_OK;
+}
+
+int svi_ls_get_membership_rows(svi_ls *h, uint32_t first, uint32_t count, uint32_t *bits) {
+  if (!h || (!bits && count)) return fail(SVI_ERR_INVALID, "svi_ls_get_membership_rows: null argument");
+  if ((uint64_t)first + count > h->P.n) return fail(SVI_ERR_INVALID, "svi_ls_get_membership_rows: rows out of range");
+  DeviceGuard guard(h->device);
+  if (count)
+    CK(cudaMemcpyAsync(bits, h->d_mbits + (size_t)first * h->P.words, (size_t)count * h->P.words * sizeof(uint32_t),
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SVI_OK;
 }
 
 int svi_ls_get_membership(svi_ls *h, uint32_t *bits) {
@@ -806,6 +1183,7 @@ int svi_ls_heldout(svi_ls *h, uint64_t npairs, const uint32_t *p, const uint32_t
   uint32_t *d_p = reinterpret_cast<uint32_t *>(d_out + npairs);
   uint32_t *d_q = d_p + npairs;
   uint8_t *d_y = reinterpret_cast<uint8_t *>(d_q + npairs);
+  if (h->share_gamma) mg_await_rows(h);
   CK(cudaMemcpyAsync(d_p, p, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(d_q, q, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(d_y, y, npairs, cudaMemcpyHostToDevice, h->stream));
@@ -836,7 +1214,8 @@ int svi_ls_device_buffer(svi_ls *h, svi_buffer which, void **dev_ptr, uint64_t *
     case SVI_BUF_MPHI: *dev_ptr = h->d_mphi; break;
     case SVI_BUF_GAMMA: *dev_ptr = h->d_gamma; break;
     case SVI_BUF_KVEC: *dev_ptr = h->d_kvec; break;
-    case SVI_BUF_CONVERGED: *dev_ptr = h->d_conv; l = 1; break;
+    // the flags the NEXT sweep reads: after this iteration's refresh that is the freshly pruned copy
+    case SVI_BUF_CONVERGED: *dev_ptr = h->d_conv2[h->conv_pending ? h->cur ^ 1 : h->cur]; l = 1; break;
     case SVI_BUF_LAMBDA: *dev_ptr = h->d_lambda; l = 2; break;
     case SVI_BUF_ACTIVE: *dev_ptr = h->d_active; l = 1; break;
     case SVI_BUF_ACTIVE_BITS: *dev_ptr = h->d_abits; l = h->P.words; break;

@@ -28,7 +28,8 @@ namespace svi {
 struct Params {
   // problem
   uint32_t n, k, ld, words;        // words = (k+31)/32
-  uint32_t node_begin, node_end;   // shard
+  uint32_t node_begin, node_end;   // node range a launch works on (the shard, or one chunk of it)
+  uint32_t shard_begin;            // first node of the handle's block: base of node_seg_lo / node_seg_up
   double alpha, eta0, eta1, ones_d;
   uint32_t k_div10;
   // graph: half-edges of the shard's nodes.  A node's list is [neighbours it does not own | neighbours it OWNS]
@@ -53,7 +54,9 @@ struct Params {
   double *lambda;   // [k*2]
   double *eb;       // [ld] exp(Elogbeta[:,0] - max)  (LOGDOM: Elogbeta[:,0])
   double *scale;    // [ld] annealing rescale ones/sum[k] (1 when not annealing)
-  uint32_t *conv;   // [n] converged (0 or c+1)
+  uint32_t *conv;   // [n] converged (0 or c+1) as this iteration's sweeps see it
+  uint32_t *conv_next;  // [n] ... as prune leaves it for the next iteration (double-buffered: the s3 sweep of this
+                        //     iteration may run after the refresh and must still see the pre-prune flags, :731-761)
   uint32_t *active; // [n] active_comms
   uint32_t *abits;  // [n*words] active-community mask
   uint32_t *mbits;  // [n*words] link-community membership
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(256) k_node(const Params P) {
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {   // the node's "lo" segments, then its "up" segments: a fixed order
       const uint32_t *off = half ? P.node_seg_up : P.node_seg_lo;
-      const uint32_t s0 = off[p - P.node_begin], s1 = off[p - P.node_begin + 1];
+      const uint32_t s0 = off[p - P.shard_begin], s1 = off[p - P.shard_begin + 1];
       for (uint32_t s = s0; s < s1; ++s) {
         const double *row = P.part + (size_t)s * P.ld;
 #pragma unroll
@@ -545,9 +548,10 @@ __global__ void __launch_bounds__(256) k_refresh(const Params P) {
     total += __shfl_xor_sync(mask, total, o);
     maxk = max(maxk, __shfl_xor_sync(mask, maxk, o));
   }
-  if (total == 1u && lane == 0) {   // sticky: never cleared (:472-473)
-    if (P.conv[p] == 0u) *P.conv_dirty = 1u;   // the neighbour lists that hold p are re-partitioned (k_partition)
-    P.conv[p] = maxk + 1u;
+  if (lane == 0) {   // sticky: never cleared (:472-473)
+    const uint32_t was = P.conv[p];
+    if (total == 1u && was == 0u) *P.conv_dirty = 1u;   // the neighbour lists that hold p are re-partitioned (k_partition)
+    P.conv_next[p] = total == 1u ? maxk + 1u : was;
   }
   if (lane == 0) P.active[p] = total;
   // active bits (only meaningful for the iter > 1000 branch; cheap enough to keep current)

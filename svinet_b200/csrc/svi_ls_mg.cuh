@@ -1,0 +1,106 @@
+// svi_ls_mg.cuh -- device side of the multi-GPU exchange over PEER MEMORY.
+//
+// Every handle keeps its exchange buffers (the replicated-layout matrices b = exp(Elogpi - max), mphi, gamma, the
+// converged flags, the active masks, K-vector slots and a flag table) in one arena; the arenas of all shards are
+// mapped into every process (CUDA IPC across processes, plain peer access inside one).  A shard PUSHES the rows it
+// produced into every peer's arena (copy engines over NVLink, on a side stream, beside the sweeps) and then raises
+// an epoch-stamped flag in the peer's flag table; consumers wait for the flags on their own stream.  The K-vector
+// all-reduces (sum, s1, s2 after the node pass; s3 after its sweep) are a push of 3 (1) x K doubles into per-source
+// slots plus a fixed-order sum on every shard -- bit-identical on all shards, no NCCL on the data path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svi {
+
+constexpr uint32_t kMaxWorld = 16;
+constexpr uint32_t kFlagKinds = 8;
+enum MgFlag : uint32_t { FLAG_B = 0, FLAG_M = 1, FLAG_KXN = 2, FLAG_KXS = 3, FLAG_G = 4 };
+
+struct Peers {
+  uint32_t world, rank;
+  unsigned char *arena[kMaxWorld];   // arena base of every shard as mapped in THIS process (own arena included)
+  uint64_t flags_off, kx_off;        // byte offsets of the flag table / K-vector slots inside an arena
+  uint32_t kx_stride;                // doubles per K-vector slot (4 * ld)
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// flag (source = this shard, kind) := epoch in every peer's table.  Launched on the stream that carried the
+// copies it announces: stream order puts it after their completion.
+static __global__ void k_mg_signal(const Peers pr, const uint32_t kind, const uint32_t epoch) {
+  const uint32_t t = threadIdx.x;
+  if (t < pr.world && t != pr.rank) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t *>(pr.arena[t] + pr.flags_off) + pr.rank * kFlagKinds + kind, epoch);
+  }
+}
+
+// wait until every peer's flag `kind` in OUR table has reached `epoch`.  Bounded: after `timeout_ns` the kernel
+// gives up and records the failure in *err (svi_ls_sync reports it) instead of hanging the GPU.
+__device__ __forceinline__ void mg_wait_flags(const Peers &pr, uint32_t kind, uint32_t epoch, uint32_t *err,
+                                              uint64_t timeout_ns) {
+  const uint32_t t = threadIdx.x;
+  if (t < pr.world && t != pr.rank) {
+    const uint32_t *f = reinterpret_cast<const uint32_t *>(pr.arena[pr.rank] + pr.flags_off) + t * kFlagKinds + kind;
+    const uint64_t t0 = global_ns();
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+      if (global_ns() - t0 > timeout_ns) {
+        atomicExch(err, 0x100u + kind * 16u + t);
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+}
+static __global__ void k_mg_wait(const Peers pr, const uint32_t kind, const uint32_t epoch, uint32_t *err,
+                                 const uint64_t timeout_ns) {
+  mg_wait_flags(pr, kind, epoch, err, timeout_ns);
+}
+
+// all-reduce, first half: our `count` doubles (count <= kx_stride) go into slot [parity][which][rank] of every
+// shard's arena (our own included), then the flag `kind` is raised.  One block.
+static __global__ void k_mg_kx_push(const Peers pr, const double *src, const uint32_t count, const uint32_t parity,
+                                    const uint32_t which, const uint32_t kind, const uint32_t epoch) {
+  const size_t slot = ((size_t)(parity * 2u + which) * kMaxWorld + pr.rank) * pr.kx_stride;
+  for (uint32_t t = 0; t < pr.world; ++t) {
+    double *dst = reinterpret_cast<double *>(pr.arena[t] + pr.kx_off) + slot;
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  const uint32_t t = threadIdx.x;
+  if (t < pr.world && t != pr.rank)
+    st_release_sys(reinterpret_cast<uint32_t *>(pr.arena[t] + pr.flags_off) + pr.rank * kFlagKinds + kind, epoch);
+}
+
+// all-reduce, second half: wait for every shard's slot, then sum them in rank order (the same order on every
+// shard: the result is bit-identical everywhere).  One block.
+static __global__ void k_mg_kx_sum(const Peers pr, double *dst, const uint32_t count, const uint32_t parity,
+                                   const uint32_t which, const uint32_t kind, const uint32_t epoch, uint32_t *err,
+                                   const uint64_t timeout_ns) {
+  mg_wait_flags(pr, kind, epoch, err, timeout_ns);
+  __syncthreads();
+  const double *base = reinterpret_cast<const double *>(pr.arena[pr.rank] + pr.kx_off) +
+                       (size_t)(parity * 2u + which) * kMaxWorld * pr.kx_stride;
+  for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
+    double s = 0.0;
+    for (uint32_t r = 0; r < pr.world; ++r) s += __ldcg(base + (size_t)r * pr.kx_stride + i);
+    dst[i] = s;
+  }
+}
+
+}  // namespace svi

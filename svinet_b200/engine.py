@@ -42,6 +42,8 @@ ABI_SYMBOLS = [
     "svi_ls_get_membership", "svi_ls_heldout", "svi_ls_get_kvectors", "svi_ls_phase_phi",
     "svi_ls_phase_node", "svi_ls_phase_s3", "svi_ls_phase_finish", "svi_ls_phase_refresh", "svi_ls_phase_lambda",
     "svi_ls_device_buffer",
+    "svi_ls_peer_blob_bytes", "svi_ls_peer_export", "svi_ls_peer_attach", "svi_ls_peer_attach_local", "svi_ls_mg_step",
+    "svi_ls_mg_share_gamma", "svi_ls_mg_error", "svi_ls_mg_timing", "svi_ls_get_membership_rows",
     "svi_ls_get_info", "svi_ls_last_error", "svi_ls_abi_version",
 ]
 
@@ -77,11 +79,21 @@ def load_library(path=None):
     L.svi_ls_phase_lambda.argtypes = [vp, C.c_int]
     L.svi_ls_device_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.svi_ls_get_info.argtypes = [vp, C.POINTER(SviInfo)]
+    L.svi_ls_peer_blob_bytes.argtypes = []
+    L.svi_ls_peer_export.argtypes = [vp, vp, C.c_size_t]
+    L.svi_ls_peer_attach.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32]
+    L.svi_ls_peer_attach_local.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32]
+    L.svi_ls_mg_step.argtypes = [vp, C.c_uint32, C.c_int, C.c_int]
+    L.svi_ls_mg_share_gamma.argtypes = [vp, C.c_int]
+    L.svi_ls_mg_error.argtypes = [vp]
+    L.svi_ls_mg_timing.argtypes = [vp, C.c_int, vp, vp]
+    L.svi_ls_get_membership_rows.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
     L.svi_ls_last_error.restype = C.c_char_p
     L.svi_ls_abi_version.restype = C.c_int
     for name in ABI_SYMBOLS:
-        if name not in ("svi_ls_destroy", "svi_ls_last_error"):
+        if name not in ("svi_ls_destroy", "svi_ls_last_error", "svi_ls_peer_blob_bytes"):
             getattr(L, name).restype = C.c_int
+    L.svi_ls_peer_blob_bytes.restype = C.c_size_t
     if path == _build.LIB:
         _lib = L
     return L
@@ -201,6 +213,53 @@ class LinkSamplingEngine:
 
     def phase_lambda(self, annealing):
         _check(self.L, self.L.svi_ls_phase_lambda(self.h, int(annealing)))
+
+    # -- multi-GPU over peer memory -----------------------------------------------------------
+    def peer_blob(self):
+        """bytes describing this shard's exchange arena (CUDA IPC handle), to be all-gathered by the caller"""
+        nb = self.L.svi_ls_peer_blob_bytes()
+        buf = np.zeros(nb, dtype=np.uint8)
+        _check(self.L, self.L.svi_ls_peer_export(self.h, _ptr(buf), nb))
+        return buf
+
+    def peer_attach(self, world, rank, bounds, blobs, chunks=0):
+        bounds = np.ascontiguousarray(bounds, dtype=np.uint32)
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8)
+        assert bounds.shape == (world + 1,) and blobs.size == world * self.L.svi_ls_peer_blob_bytes()
+        _check(self.L, self.L.svi_ls_peer_attach(self.h, world, rank, _ptr(bounds), _ptr(blobs), chunks))
+
+    @staticmethod
+    def attach_local(engines, bounds, chunks=0):
+        """all shards live in this process (one or several devices)"""
+        world = len(engines)
+        bounds = np.ascontiguousarray(bounds, dtype=np.uint32)
+        arr = (C.c_void_p * world)(*[e.h.value for e in engines])
+        for r, e in enumerate(engines):
+            _check(e.L, e.L.svi_ls_peer_attach_local(e.h, world, r, _ptr(bounds), C.cast(arr, C.c_void_p), chunks))
+
+    def mg_step(self, it, annealing, write_comm):
+        _check(self.L, self.L.svi_ls_mg_step(self.h, it, int(annealing), int(write_comm)))
+
+    def mg_share_gamma(self, on=True):
+        _check(self.L, self.L.svi_ls_mg_share_gamma(self.h, int(on)))
+
+    MG_PHASES = ("wait_b_rows", "phi+node", "allreduce_sum_s1_s2", "refresh", "wait_mphi_rows", "s3", "allreduce_s3+lambda",
+                 "drain_own_pushes")
+
+    def mg_timing(self, enable=True, read=False):
+        """enable/disable per-phase timing of mg_step; read=True returns {phase: mean ms} over the recorded steps"""
+        if not read:
+            _check(self.L, self.L.svi_ls_mg_timing(self.h, int(enable), None, None))
+            return None
+        ms = np.zeros(8, dtype=np.float64)
+        cnt = C.c_uint32()
+        _check(self.L, self.L.svi_ls_mg_timing(self.h, int(enable), _ptr(ms), C.byref(cnt)))
+        return dict(zip(self.MG_PHASES, [float(x) for x in ms])), cnt.value
+
+    def membership_rows(self, first, count):
+        bits = np.empty((count, self.words), dtype=np.uint32)
+        _check(self.L, self.L.svi_ls_get_membership_rows(self.h, first, count, _ptr(bits)))
+        return bits
 
     def membership_bits(self):
         bits = np.empty((self.n, self.words), dtype=np.uint32)

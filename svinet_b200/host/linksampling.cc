@@ -145,14 +145,7 @@ LinkSampling::LinkSampling(Env &env, Network &network)
   lap("assign_training_links");
   if (env_.dump_only) return;
 
-  svi_ls_config cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.n = n_; cfg.k = k_; cfg.nlinks = links_.size() / 2;
-  cfg.alpha = env_.alpha; cfg.eta0 = env_.eta0; cfg.eta1 = env_.eta1;
-  cfg.ones = net_.ones(); cfg.device = -1; cfg.seg_len = 0;
-  cfg.node_begin = 0; cfg.node_end = n_;
-  DEV(svi_ls_create(&cfg, links_.data(), training_links_.data(), &dev_));
-  DEV(svi_ls_set_state(dev_, gamma_.data(), lambda_.data()));
+  create_device();
   lap("svi_ls_create + set_state");
 
   // held-out pairs in std::map<Edge,bool> order (lexicographic), the order validation_likelihood sums in
@@ -174,7 +167,75 @@ LinkSampling::~LinkSampling() {
   if (vf_) fclose(vf_);
   if (tf_) fclose(tf_);
   if (lf_) fclose(lf_);
-  if (dev_) svi_ls_destroy(dev_);
+  for (svi_ls *d : devs_) svi_ls_sync(d);      // no shard may vanish while a peer still pushes rows into it
+  for (svi_ls *d : devs_) svi_ls_destroy(d);
+}
+
+// The device side of the object: one handle, or with -gpus N one handle per GPU, each owning an edge-balanced
+// contiguous node block; the shards exchange rows over peer memory inside svi_ls_mg_step.
+// The seam stays src/main.cc:337-341: one LinkSampling object driven by one host thread.
+void LinkSampling::create_device() {
+  const uint32_t g = (uint32_t)std::max(1, env_.ngpus);
+  svi_ls_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.n = n_; cfg.k = k_; cfg.nlinks = links_.size() / 2;
+  cfg.alpha = env_.alpha; cfg.eta0 = env_.eta0; cfg.eta1 = env_.eta1;
+  cfg.ones = net_.ones(); cfg.device = -1; cfg.seg_len = 0;
+  cfg.node_begin = 0; cfg.node_end = n_;
+  devs_.assign(g, nullptr);
+  if (g == 1) {
+    DEV(svi_ls_create(&cfg, links_.data(), training_links_.data(), &devs_[0]));
+    dev_ = devs_[0];
+    DEV(svi_ls_set_state(dev_, gamma_.data(), lambda_.data()));
+    return;
+  }
+  // node blocks holding ~1/g of the half-edges each (training_links_[v] = 2 x degree)
+  bounds_.assign(g + 1, n_);
+  bounds_[0] = 0;
+  double total = 0, run = 0;
+  for (uint32_t v = 0; v < n_; ++v) total += training_links_[v];
+  uint32_t r = 1;
+  for (uint32_t v = 0; v < n_ && r < g; ++v) {
+    while (r < g && run >= total * r / g) bounds_[r++] = v;
+    run += training_links_[v];
+  }
+  // the shards are built concurrently (each uploads the link list to its GPU and sorts its half-edges there)
+  std::vector<int> rc(g, 0);
+  std::vector<std::string> msg(g);
+  std::vector<std::thread> th;
+  for (uint32_t i = 0; i < g; ++i)
+    th.emplace_back([&, i] {
+      svi_ls_config c = cfg;
+      c.device = (int32_t)i;
+      c.node_begin = bounds_[i];
+      c.node_end = bounds_[i + 1];
+      rc[i] = svi_ls_create(&c, links_.data(), training_links_.data(), &devs_[i]);
+      if (rc[i]) msg[i] = svi_ls_last_error();
+    });
+  for (auto &t : th) t.join();
+  for (uint32_t i = 0; i < g; ++i)
+    if (rc[i]) {
+      fprintf(stderr, "svinet: svi_ls_create on GPU %u failed: %s\n", i, msg[i].c_str());
+      exit(-1);
+    }
+  dev_ = devs_[0];
+  for (uint32_t i = 0; i < g; ++i) {
+    DEV(svi_ls_peer_attach_local(devs_[i], g, i, bounds_.data(), devs_.data(), 0));
+    DEV(svi_ls_mg_share_gamma(devs_[i], 1));   // shard 0 evaluates the held-out pairs and writes the model
+  }
+  for (uint32_t i = 0; i < g; ++i) DEV(svi_ls_set_state(devs_[i], gamma_.data(), lambda_.data()));
+}
+
+void LinkSampling::device_step(bool write_comm) {
+  if (devs_.size() == 1) {
+    DEV(svi_ls_step(dev_, iter_, annealing_ ? 1 : 0, write_comm ? 1 : 0));
+    return;
+  }
+  for (svi_ls *d : devs_) DEV(svi_ls_mg_step(d, iter_, annealing_ ? 1 : 0, write_comm ? 1 : 0));
+}
+
+void LinkSampling::device_sync() {
+  for (svi_ls *d : devs_) DEV(svi_ls_sync(d));
 }
 
 bool LinkSampling::edge_ok(const Edge &e) const {
@@ -454,7 +515,13 @@ void LinkSampling::write_communities(const std::string &name) {
   // (a permutation computed once), so every community's list comes out sorted without a per-report sort.
   const uint32_t words = (k_ + 31) / 32;
   if (member_bits_.size() != (size_t)n_ * words) member_bits_.assign((size_t)n_ * words, 0);
-  if (have_membership_) DEV(svi_ls_get_membership(dev_, member_bits_.data()));
+  if (have_membership_) {
+    if (devs_.size() == 1) DEV(svi_ls_get_membership(dev_, member_bits_.data()));
+    else   // every shard holds the membership words of its own node block
+      for (size_t i = 0; i < devs_.size(); ++i)
+        DEV(svi_ls_get_membership_rows(devs_[i], bounds_[i], bounds_[i + 1] - bounds_[i],
+                                       member_bits_.data() + (size_t)bounds_[i] * words));
+  }
   if (by_id_.size() != n_) {
     by_id_.resize(n_);
     for (uint32_t p = 0; p < n_; ++p) by_id_[p] = p;
@@ -540,8 +607,8 @@ void LinkSampling::infer() {
     printf("\riteration %d: processing %zu links", iter_, links_.size() / 2);
     fflush(stdout);
     auto t0 = std::chrono::steady_clock::now();
-    DEV(svi_ls_step(dev_, iter_, annealing_ ? 1 : 0, write_comm ? 1 : 0));
-    if (lap.on) { DEV(svi_ls_sync(dev_)); t_step += since(t0); }
+    device_step(write_comm);
+    if (lap.on) { device_sync(); t_step += since(t0); }
     if (write_comm) have_membership_ = true;
 
     if (env_.terminate) {             // SIGTERM: dump the model and carry on (:763-766)

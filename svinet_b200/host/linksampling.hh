@@ -74,7 +74,12 @@ class LinkSampling {
   uint32_t nh_ = 0;
   time_t start_time_;
   FILE *vf_ = nullptr, *tf_ = nullptr, *lf_ = nullptr;
-  svi_ls *dev_ = nullptr;
+  svi_ls *dev_ = nullptr;                 // shard 0 (the only one without -gpus N)
+  std::vector<svi_ls *> devs_;            // -gpus N: one handle per GPU, node-block shards (include/svi_ls.h, svi_ls_mg_step)
+  std::vector<uint32_t> bounds_;          // [ngpus+1] node blocks of the shards
+  void create_device();
+  void device_step(bool write_comm);
+  void device_sync();
   // held-out pairs in evaluation order, flattened for svi_ls_heldout
   std::vector<uint32_t> hp_, hq_;
   std::vector<uint8_t> hy_;

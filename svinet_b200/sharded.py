@@ -19,6 +19,15 @@ has three real exchange steps, done with NCCL over NVLink/NVSwitch:
 The row all-gathers are the only bulk traffic: 2 x N*K*8 bytes per iteration (3.2 GB at n=1M, k=200)
 against ~480 GB of local HBM traffic divided by the number of GPUs.
 
+Two exchange mechanisms:
+  * exchange="peer" (default on CUDA): the whole iteration incl. its exchanges runs inside the C library
+    (svi_ls_mg_step, include/svi_ls.h): rows are pushed into the peers' arenas over NVLink by the copy engines beside
+    the sweeps (the mphi rows of a finished chunk beside the next chunk's phi sweep, the exp(Elogpi) rows beside the
+    s3 sweep), announced by epoch flags; K-vectors are reduced through per-source slots in a fixed order.
+    torch.distributed only carries the CUDA IPC handles at start-up and the timing barriers.
+  * exchange="nccl": the choreography below over torch.distributed collectives -- the round-1 path, kept as the
+    library baseline to compare against and as what the CPU (gloo) tests drive.
+
 The collective choreography is independent of what executes the phases: `engine_factory` lets the CPU
 tests (gloo, world_size 2) drive it with a numpy stand-in; the product path builds the CUDA engine and
 refuses to run without a GPU.
@@ -88,8 +97,14 @@ class CudaShardEngine:
 
 class ShardedLinkSampling:
     def __init__(self, n, k, links, rank, world, device=0, stream=None, engine_factory=None, group=None,
-                 overlap=True, **kw):
+                 overlap=True, exchange=None, ones=None, chunks=0, share_gamma=False, **kw):
         self.n, self.k, self.rank, self.world, self.group = n, k, rank, world, group
+        if exchange is None:
+            exchange = "peer" if (engine_factory is None and torch.cuda.is_available()) else "nccl"
+        self.exchange = exchange
+        if exchange == "peer":
+            self._init_peer(n, k, links, rank, world, device, stream, ones, chunks, share_gamma, kw)
+            return
         # overlap=True: the iteration order of _step_overlapped; over NCCL the bulk row exchanges additionally get
         # their own communicator and a side stream so that they run beside the kernels
         self.overlap = overlap
@@ -106,11 +121,41 @@ class ShardedLinkSampling:
         tl = 2.0 * np.bincount(links.ravel().astype(np.int64), minlength=n).astype(np.float64)
         mine = ((links[:, 0] >= nb) & (links[:, 0] < ne)) | ((links[:, 1] >= nb) & (links[:, 1] < ne))
         factory = engine_factory or CudaShardEngine
-        self.eng = factory(n, k, links[mine], (nb, ne), device, stream, tl=tl, ones=links.shape[0], **kw)
+        # `ones` = the reference's _network.ones(): ALL links incl. held-out ones (numerator of the annealing rescale,
+        # src/linksampling.cc:541-542); defaults to the training-link count
+        self.eng = factory(n, k, links[mine], (nb, ne), device, stream, tl=tl,
+                           ones=(links.shape[0] if ones is None else ones), **kw)
         self.nlinks = links.shape[0]
         self.local_half_edges = int(tl[nb:ne].sum() // 2)
         self._buf = {name: self.eng.buffer(name) for name in
-                     ("exppi", "mphi", "gamma", "kvec", "converged", "active", "active_bits", "member_bits")}
+                     ("exppi", "mphi", "gamma", "kvec", "active", "active_bits", "member_bits")}
+
+    def _init_peer(self, n, k, links, rank, world, device, stream, ones, chunks, share_gamma, kw):
+        """Product path: one CUDA engine per rank, arenas exchanged as CUDA IPC handles, svi_ls_mg_step."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("svinet_b200.sharded: no CUDA device; the product path has no CPU fallback")
+        from .engine import LinkSamplingEngine
+        links = np.ascontiguousarray(links, dtype=np.uint32).reshape(-1, 2)
+        self.bounds = plan_shards(n, links, world)
+        nb, ne = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        # the WHOLE link list goes to the library: the device-side CSR build keeps the half-edges of this block
+        self.eng = LinkSamplingEngine(n, k, links, device=device, node_range=(nb, ne), stream=stream,
+                                      ones=(links.shape[0] if ones is None else ones), **kw)
+        self.nlinks = links.shape[0]
+        self.local_half_edges = int(self.eng.info()["half_edges_phi"])
+        blob = torch.from_numpy(self.eng.peer_blob())
+        if world > 1:
+            dev = torch.device("cuda", device)
+            mine = blob.to(dev)
+            allb = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allb, mine, group=self.group)
+            blobs = torch.stack(allb).cpu().numpy()
+        else:
+            blobs = blob.numpy()[None]
+        self.eng.peer_attach(world, rank, self.bounds, blobs, chunks=chunks)
+        if share_gamma:
+            self.eng.mg_share_gamma(True)
+        self.share_gamma = share_gamma
 
     # ---- collectives on the engine's own buffers ----
     def _allreduce(self, t):
@@ -123,7 +168,8 @@ class ShardedLinkSampling:
         point-to-point transfers (every rank sends its block to every peer and receives theirs), so all
         NVLink ports work at once; a sequence of `world` broadcasts (the gloo path of the CPU tests)
         serialises them and measured 2x slower at 8 GPUs."""
-        buf = self._buf[name]
+        # (`converged` is double-buffered inside the library: ask for the current pointer every time)
+        buf = self._buf[name] if name in self._buf else self.eng.buffer(name)
         group = self.bulk_group if (bulk and self.bulk_group is not None) else self.group
         blocks = [buf[int(self.bounds[r]):int(self.bounds[r + 1])] for r in range(self.world)]
         if dist.get_backend(self.group) == "nccl" and self.world > 1:
@@ -149,6 +195,8 @@ class ShardedLinkSampling:
         self.eng.set_state(gamma, lam)     # derives the factors of ALL rows, no exchange needed
 
     def step(self, it, annealing, write_comm, events=None, stream=None):
+        if self.exchange == "peer":
+            return self.eng.mg_step(it, annealing, write_comm)
         if self.overlap:
             return self._step_overlapped(it, annealing, write_comm, events, stream)
 
@@ -230,6 +278,10 @@ class ShardedLinkSampling:
 
     def gather_state(self):
         """Full gamma [n,k] and lambda [k,2] on every rank (for save_model / parity checks)."""
+        if self.exchange == "peer":
+            if not self.share_gamma:
+                raise RuntimeError("gather_state over the peer exchange needs share_gamma=True")
+            return self.eng.get_state()
         self._allgather_rows("gamma")
         return self.eng.get_state()
 
@@ -259,9 +311,16 @@ class ShardedLinkSampling:
             for _ in range(1 if not timed else steps):
                 step_fn(it)
                 it += 1
-                self._allgather_rows("gamma")
-                ll = self.eng.heldout(hp, hq, hy)
-                bits = self.eng.membership_bits()
+                if self.exchange == "peer":
+                    # gamma rows were pushed by the step itself (share_gamma); only this rank's block of the
+                    # membership words is read back
+                    ll = self.eng.heldout(hp, hq, hy)
+                    nb, ne = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+                    bits = self.eng.membership_rows(nb, ne - nb)
+                else:
+                    self._allgather_rows("gamma")
+                    ll = self.eng.heldout(hp, hq, hy)
+                    bits = self.eng.membership_bits()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)
@@ -269,5 +328,8 @@ class ShardedLinkSampling:
         return {"value": nlinks * steps / float(t.item()), "unit": unit, "steps": steps,
                 "h2d_bytes_per_step": int(hp.nbytes + hq.nbytes + hy.nbytes),
                 "d2h_bytes_per_step": int(ll.nbytes + bits.nbytes),
-                "what": "per rank and iteration: sharded step (NCCL exchanges) + gamma row all-gather + "
-                        "svi_ls_heldout on 1/world of the pairs (host in/out) + svi_ls_get_membership (host bits)"}
+                "what": ("per rank and iteration: svi_ls_mg_step (peer-memory exchanges, gamma rows shared) + "
+                         "svi_ls_heldout on 1/world of the pairs (host in/out) + svi_ls_get_membership_rows of the "
+                         "rank's own block (host bits)") if self.exchange == "peer" else
+                        ("per rank and iteration: sharded step (NCCL exchanges) + gamma row all-gather + "
+                         "svi_ls_heldout on 1/world of the pairs (host in/out) + svi_ls_get_membership (host bits)")}

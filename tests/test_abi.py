@@ -69,7 +69,7 @@ def test_abi_is_usable_from_plain_c(lib, tmp_path):
 
 
 def test_abi_version(lib):
-    assert lib.svi_ls_abi_version() == 1
+    assert lib.svi_ls_abi_version() == 2
 
 
 def test_invalid_arguments_are_rejected(lib):

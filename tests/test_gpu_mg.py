@@ -1,0 +1,95 @@
+"""The sharded CUDA path (svi_ls_mg_step: node-block shards exchanging rows over peer memory, include/svi_ls.h)
+against the oracle ON HARDWARE -- needs one B200.
+
+All shards live in this process and on the same device (svi_ls_peer_attach_local): the kernels restricted to a node
+block, the chunked phi/node pipeline, the refresh-before-s3 order with the double-buffered converged flags, the row
+pushes, the flag protocol and the slot all-reduces are exactly the code the multi-GPU runs execute; only the copies
+stay inside one GPU.  (bench.py under torchrun runs the same calls with one process per GPU and CUDA IPC; its
+state checksum must equal the single-GPU one, see bench.py --checksum.)
+"""
+import numpy as np
+import pytest
+
+import oracle_py as orc
+from svinet_b200 import synth
+from svinet_b200.engine import LinkSamplingEngine
+from svinet_b200.sharded import plan_shards
+from test_gpu_parity import TOL, rel_err
+from test_gpu_parity_ring import oracle_state
+
+pytestmark = pytest.mark.gpu
+
+
+def run_sharded_vs_oracle(n, k, links, gamma, conv, world, chunks, sched, seg_len=0):
+    st = oracle_state(n, k, links, gamma, np.ones((k, 2)), conv)
+    bounds = plan_shards(n, links, world)
+    engines = [LinkSamplingEngine(n, k, links, node_range=(int(bounds[r]), int(bounds[r + 1])), seg_len=seg_len)
+               for r in range(world)]
+    LinkSamplingEngine.attach_local(engines, bounds, chunks=chunks)
+    for e in engines:
+        e.mg_share_gamma(True)
+        e.set_state(st.arr("gamma"), st.arr("lambda_"))
+        e.set_converged(st.arr("converged"))
+    for it, ann, wc in sched:
+        st.step(it, ann, wc)
+        for e in engines:
+            e.mg_step(it, ann, wc)
+        for e in engines:
+            e.sync()
+        mem = np.zeros((n, k), dtype=np.uint8)
+        for r, e in enumerate(engines):
+            tag = "world=%d shard %d iter %d" % (world, r, it)
+            g, lam = e.get_state()
+            assert rel_err(g, st.arr("gamma")) <= TOL, tag
+            assert rel_err(lam, st.arr("lambda_")) <= TOL, tag
+            kv = e.kvectors()
+            for name in ("sum", "s1", "s2", "s3"):
+                want = st.arr(name)
+                assert rel_err(kv[name], want, floor=max(1e-12, 1e-6 * float(np.max(np.abs(want))))) <= TOL, (tag, name)
+            cv, act = e.get_converged()
+            assert np.array_equal(cv, st.arr("converged")), tag
+            nb, ne = int(bounds[r]), int(bounds[r + 1])
+            assert np.array_equal(act[nb:ne], st.arr("active_comms")[nb:ne]), tag
+            if wc:
+                bits = e.membership_rows(nb, ne - nb)
+                cols = np.arange(k)
+                mem[nb:ne] = (bits[:, cols // 32] >> (cols % 32).astype(np.uint32)) & 1
+        if wc:
+            assert np.array_equal(mem, st.arr("member")), "membership, iter %d" % it
+        # every shard ends the iteration with bit-identical replicated state
+        g0, l0 = engines[0].get_state()
+        for e in engines[1:]:
+            g, lam = e.get_state()
+            assert np.array_equal(g, g0) and np.array_equal(lam, l0)
+    shortcut = st.c.cnt_shortcut
+    for e in engines:
+        e.close()
+    st.free()
+    return shortcut
+
+
+@pytest.mark.parametrize("world,k,chunks", [(2, 12, 1), (2, 200, 4), (3, 100, 3), (4, 64, 2)])
+def test_shards_on_one_gpu_match_oracle(world, k, chunks):
+    n = 900
+    links = synth.mmsb_links(n, k, 30 * n, seed=50 + k)
+    gamma, _ = synth.random_state(n, k, links, seed=k)
+    rng = np.random.default_rng(world)
+    conv = np.zeros(n, dtype=np.uint32)
+    who = rng.random(n) < 0.25
+    conv[who] = rng.integers(1, k + 1, who.sum())
+    sched = [(0, 1, 0), (1, 1, 1), (2, 0, 1), (3, 0, 0), (4, 1, 1)]
+    assert run_sharded_vs_oracle(n, k, links, gamma, conv, world, chunks, sched, seg_len=64) > 0
+
+
+def test_shards_where_nodes_converge_on_the_way():
+    """assort-75-4 converges node after node: the flags pruned by one shard must reach the others' next sweep, and
+    the s3 sweep of the SAME iteration must still see the pre-prune flags (src/linksampling.cc:731-761)."""
+    from golden_util import Scratch, input_path
+    with Scratch() as d:
+        g = orc.Graph.read(input_path("assort-75-4.txt", d), 75)
+        m = orc.Model(g, 4, use_validation_stop=0)
+        st = m.state
+        links, gamma = st.arr("links").copy(), st.arr("gamma").copy()
+        m.close(); g.close()
+    sched = [(it, it < 14, 1) for it in range(28)]
+    run_sharded_vs_oracle(75, 4, links, gamma, np.zeros(75, dtype=np.uint32), 3, 2, sched)

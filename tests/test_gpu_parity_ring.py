@@ -65,7 +65,7 @@ def test_ring_sweeps_long_segments_hub_and_converged(k):
     for e in engines:
         info = e.info()
         assert info["ring_depth"] > 0, "K=%d must run the ring sweeps" % k
-    assert engines[1].info()["segments_phi"] > 4 * n     # degree ~300 in ragged pieces of <= 37 neighbours
+    assert engines[1].info()["segments_phi"] > 3 * n     # degrees in the hundreds in ragged pieces of <= 37 neighbours
     assert engines[2].info()["seg_len"] == 1024          # clamped: the hub's two parts hold ~1000 rows each
     for it, ann, wc in [(0, 1, 0), (1, 1, 1), (2, 0, 1)]:
         st.step(it, ann, wc)
