@@ -64,12 +64,22 @@ struct Ops {
   void (*phi_ring)(const Params &, cudaStream_t, bool sparse, bool comm, uint32_t seg_first, uint32_t seg_end,
                    uint32_t publish) = nullptr;
   void (*s3_ring)(const Params &, cudaStream_t, uint32_t blocks) = nullptr;
+  void (*preload)() = nullptr;            // force-load every kernel of the tile (see preload_common)
   void (*prepare_phi_ring)() = nullptr;   // per-device function attributes (dynamic shared memory), once per handle
   void (*prepare_s3_ring)() = nullptr;
   int (*max_blocks_s3_ring)(int sms, uint32_t ld) = nullptr;
   int ring_lanes = 0, ring_vec = 0, ring_depth = 0, ring_threads = 256;   // tiling of phi_ring
   int s3_lanes = 0, s3_vec = 0, s3_threads = 256;                         // tiling of s3_ring (may differ)
 };
+
+// CUDA loads kernels lazily, on their first launch, and that load can wait for running kernels to finish.  A shard
+// whose stream sits in a flag wait (svi_ls_mg.cuh) while its host thread launches a never-loaded kernel would then
+// dead-lock with its peers, so every kernel is loaded when the handle is created.
+template <class K>
+void touch(K kern) {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, (const void *)kern);
+}
 
 constexpr int kThreads = 256;
 constexpr uint32_t kMaxChunks = 8;   // pipeline chunks of a shard's node block in svi_ls_mg_step
@@ -118,8 +128,22 @@ struct Tile {
   }
   static int max_blocks_node(int sms) { return occ((const void *)svi::k_node<G, V>, sms); }
   static int max_blocks_s3(int sms) { return occ((const void *)svi::k_s3<G, V>, sms); }
+  static void preload() {
+    touch(svi::k_phi<G, V, L, false, false>);
+    touch(svi::k_phi<G, V, L, false, true>);
+    touch(svi::k_phi<G, V, L, true, false>);
+    touch(svi::k_phi<G, V, L, true, true>);
+    touch(svi::k_node<G, V>);
+    touch(svi::k_s3<G, V>);
+    touch(svi::k_lambda<L>);
+    touch(svi::k_refresh<G, V, L, true>);
+    touch(svi::k_refresh<G, V, L, false>);
+    touch(svi::k_heldout<G, V>);
+  }
   static Ops ops() {
-    return Ops{phi, node, s3, lambda, refresh, heldout, max_blocks_node, max_blocks_s3, G, V, L ? 1 : 0};
+    Ops o{phi, node, s3, lambda, refresh, heldout, max_blocks_node, max_blocks_s3, G, V, L ? 1 : 0};
+    o.preload = preload;
+    return o;
   }
 };
 
@@ -587,8 +611,12 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   else
     h->blocks_s3 = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ops.max_blocks_s3(h->sms),
                                                                    ((int64_t)nseg3 * ops.lanes + kThreads - 1) / kThreads));
-  if (ops.prepare_phi_ring) ops.prepare_phi_ring();
+  if (ops.prepare_phi_ring) ops.prepare_phi_ring();   // (setting the attribute loads the ring kernels too)
   if (ops.prepare_s3_ring) ops.prepare_s3_ring();
+  if (ops.preload) ops.preload();
+  touch(svi::k_reduce_kpart); touch(svi::k_scale); touch(svi::k_partition); touch(svi::k_fill);
+  touch(svi::k_pad_rows); touch(svi::k_unpad_rows);
+  touch(svi::k_mg_signal); touch(svi::k_mg_wait); touch(svi::k_mg_kx_push); touch(svi::k_mg_kx_sum);
   h->kpart_blocks = std::max(h->blocks_node, h->blocks_s3);
   const size_t cap = std::max(2 * (size_t)ops.lanes * ops.vec, 2 * (size_t)ops.s3_lanes * ops.s3_vec);
   cudaError_t e = cudaSuccess;
@@ -960,6 +988,11 @@ static int mg_finish_attach(svi_ls *h, uint32_t world, uint32_t rank, const uint
     h->chunk_nodes.push_back(std::max(h->chunk_nodes.back(), h->P.node_begin + v));
   }
   h->chunk_nodes.push_back(h->P.node_end);
+  // first use of the copy / memset paths between the arenas happens here, not beside a waiting kernel
+  for (uint32_t r = 0; r < world; ++r)
+    if (r != rank) CK(cudaMemcpyAsync(h->d_mg_err, h->peers.arena[r] + h->lay.flags, sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->side));
+  CK(cudaMemsetAsync(h->d_mg_err, 0, sizeof(uint32_t), h->side));
+  CK(cudaStreamSynchronize(h->side));
   h->epoch = 0;
   h->mg = true;
   h->partition_every_sweep = world > 1;

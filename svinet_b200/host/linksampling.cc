@@ -200,13 +200,16 @@ void LinkSampling::create_device() {
     run += training_links_[v];
   }
   // the shards are built concurrently (each uploads the link list to its GPU and sorts its half-edges there)
+  // (SVINET_SHARDS_ON_ONE_GPU=1: all shards on the current device -- the same code path on a one-GPU box)
+  const char *same = getenv("SVINET_SHARDS_ON_ONE_GPU");
+  const bool one_gpu = same && same[0] == '1';
   std::vector<int> rc(g, 0);
   std::vector<std::string> msg(g);
   std::vector<std::thread> th;
   for (uint32_t i = 0; i < g; ++i)
     th.emplace_back([&, i] {
       svi_ls_config c = cfg;
-      c.device = (int32_t)i;
+      c.device = one_gpu ? -1 : (int32_t)i;
       c.node_begin = bounds_[i];
       c.node_end = bounds_[i + 1];
       rc[i] = svi_ls_create(&c, links_.data(), training_links_.data(), &devs_[i]);

@@ -22,14 +22,15 @@ def cli():
     return path
 
 
-def run_case(cli, case, d):
+def run_case(cli, case, d, extra=(), env=None):
     ent = MANIFEST[case]
     inp = input_path(ent["input"], d)
     local = os.path.join(d, ent["input"])
     if not os.path.exists(local):
         os.symlink(inp, local)
-    cmd = [cli, "-file", ent["input"], "-n", str(ent["n"]), "-k", str(ent["k"]), "-link-sampling"] + ent["flags"]
-    p = subprocess.run(cmd, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=600)
+    cmd = [cli, "-file", ent["input"], "-n", str(ent["n"]), "-k", str(ent["k"]), "-link-sampling"] + ent["flags"] + list(extra)
+    p = subprocess.run(cmd, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=600,
+                       env=dict(os.environ, **(env or {})))
     assert p.returncode == 0, p.stderr.decode()
     return ent, os.path.join(d, ent["outdir"])
 
@@ -62,6 +63,26 @@ def test_cli_output_directory_matches_reference(cli, case):
         assert noff <= max(2, nf // 1000), flips
         for f in ("infer.log", "logl.txt", "test-edges.txt", "network.dat"):
             assert os.path.lexists(os.path.join(out, f)), f
+
+
+@pytest.mark.parametrize("case,gpus", [("c1_m30", 3), ("c1_natural", 2), ("lfr_k28_m20", 4), ("c2_m25", 2)])
+def test_cli_gpus_n_writes_the_reference_directory(cli, case, gpus):
+    """`svinet -link-sampling -gpus N` (node-block shards exchanging rows over peer memory, one host thread; the seam
+    is src/main.cc:337-341) against the same reference fixtures as the single-GPU run.  On a one-GPU box the shards
+    share the device (SVINET_SHARDS_ON_ONE_GPU=1): same code path, copies stay on the GPU."""
+    import torch
+    env = {} if torch.cuda.device_count() >= gpus else {"SVINET_SHARDS_ON_ONE_GPU": "1"}
+    with Scratch() as d:
+        ent, out = run_case(cli, case, d, extra=["-gpus", str(gpus)], env=env)
+        flips = {}
+        for fname in ("gamma.txt", "lambda.txt", "groups.txt", "validation.txt", "max.txt"):
+            got = open(os.path.join(out, fname)).read()
+            flips[fname] = compare_numeric_text(got, golden_text(case, fname),
+                                                skip_cols=(1,) if fname in ("validation.txt", "max.txt") else ())
+        for fname in ("communities.txt", "validation-edges.txt"):
+            assert open(os.path.join(out, fname)).read() == golden_text(case, fname), fname
+        nf, noff = flips["gamma.txt"]
+        assert noff <= max(2, nf // 1000), flips
 
 
 FA2_CASES = [c for c in MANIFEST if MANIFEST[c].get("mode") == "-rnode -stratified"]
