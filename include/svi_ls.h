@@ -168,12 +168,13 @@ int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm);
 int svi_ls_mg_share_gamma(svi_ls *h, int on);
 int svi_ls_mg_error(svi_ls *h);
 /* Per-phase device times of svi_ls_mg_step, measured with events on the handle's stream: enable, run steps, then
- * read the mean over the (at most 32) last steps into phase_ms[8]:
+ * read the mean over the (at most 32) last steps into phase_ms[10]:
  *   [0] wait for the peers' exp(Elogpi)/converged rows   (exposed exchange)
  *   [1] partition + phi sweep + mean indicators, chunked  [2] all-reduce sum,s1,s2
  *   [3] refresh                                           [4] wait for the peers' mphi rows (exposed exchange)
  *   [5] s3 sweep                                          [6] all-reduce s3 + lambda
- *   [7] wait for the own pushes to drain                  (exposed exchange) */
+ *   [7] wait for the own pushes to drain                  (exposed exchange)
+ *   [8] side stream: first mphi push .. mphi flag raised  [9] side stream: first exp(Elogpi) push .. flag raised */
 int svi_ls_mg_timing(svi_ls *h, int enable, double *phase_ms, uint32_t *steps);
 /* membership words of the rows [first, first+count) only (a shard's own block) */
 int svi_ls_get_membership_rows(svi_ls *h, uint32_t first, uint32_t count, uint32_t *bits);

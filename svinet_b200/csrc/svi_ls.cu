@@ -50,7 +50,8 @@ using svi::s3_owner;
 struct Ops {
   // phi sweep over segments [seg_first, seg_end); comm: with the link-community tally; publish: the tally also sets the
   // neighbour's bit (one arg-max per link)
-  void (*phi)(const Params &, cudaStream_t, bool sparse, bool comm, uint32_t seg_first, uint32_t seg_end, uint32_t publish);
+  void (*phi)(const Params &, cudaStream_t, bool sparse, bool comm, uint32_t seg_first, uint32_t seg_end,
+              uint32_t seg_first2, uint32_t seg_end2, uint32_t publish);
   void (*node)(const Params &, cudaStream_t, uint32_t blocks);
   void (*s3)(const Params &, cudaStream_t, uint32_t blocks);
   void (*lambda)(const Params &, cudaStream_t, int annealing, int update);
@@ -62,7 +63,7 @@ struct Ops {
   int lanes, vec, logdom;
   // second-generation sweeps (svi_ls_ring.cuh), present for 32 < K <= 256
   void (*phi_ring)(const Params &, cudaStream_t, bool sparse, bool comm, uint32_t seg_first, uint32_t seg_end,
-                   uint32_t publish) = nullptr;
+                   uint32_t seg_first2, uint32_t seg_end2, uint32_t publish) = nullptr;
   void (*s3_ring)(const Params &, cudaStream_t, uint32_t blocks) = nullptr;
   void (*preload)() = nullptr;            // force-load every kernel of the tile (see preload_common)
   void (*prepare_phi_ring)() = nullptr;   // per-device function attributes (dynamic shared memory), once per handle
@@ -89,13 +90,15 @@ struct Tile {
   static constexpr int CAP = 2 * G * V;
   static constexpr size_t kSmem = (size_t)(kThreads / G) * CAP * sizeof(double);
 
-  static void phi(const Params &P, cudaStream_t st, bool sparse, bool comm, uint32_t s0, uint32_t s1, uint32_t pub) {
-    if (s1 <= s0) return;
-    const uint32_t blocks = (uint32_t)(((uint64_t)(s1 - s0) * G + kThreads - 1) / kThreads);
-    if (sparse && comm) svi::k_phi<G, V, L, true, true><<<blocks, kThreads, 0, st>>>(P, s0, s1, pub);
-    else if (sparse) svi::k_phi<G, V, L, true, false><<<blocks, kThreads, 0, st>>>(P, s0, s1, pub);
-    else if (comm) svi::k_phi<G, V, L, false, true><<<blocks, kThreads, 0, st>>>(P, s0, s1, pub);
-    else svi::k_phi<G, V, L, false, false><<<blocks, kThreads, 0, st>>>(P, s0, s1, pub);
+  static void phi(const Params &P, cudaStream_t st, bool sparse, bool comm, uint32_t s0, uint32_t s1, uint32_t t0,
+                  uint32_t t1, uint32_t pub) {
+    const uint64_t cnt = (uint64_t)(s1 - s0) + (t1 - t0);
+    if (!cnt) return;
+    const uint32_t blocks = (uint32_t)((cnt * G + kThreads - 1) / kThreads);
+    if (sparse && comm) svi::k_phi<G, V, L, true, true><<<blocks, kThreads, 0, st>>>(P, s0, s1, t0, t1, pub);
+    else if (sparse) svi::k_phi<G, V, L, true, false><<<blocks, kThreads, 0, st>>>(P, s0, s1, t0, t1, pub);
+    else if (comm) svi::k_phi<G, V, L, false, true><<<blocks, kThreads, 0, st>>>(P, s0, s1, t0, t1, pub);
+    else svi::k_phi<G, V, L, false, false><<<blocks, kThreads, 0, st>>>(P, s0, s1, t0, t1, pub);
   }
   static void node(const Params &P, cudaStream_t st, uint32_t blocks) {
     svi::k_node<G, V><<<blocks, kThreads, kSmem, st>>>(P);
@@ -165,17 +168,19 @@ struct RingTile {
     prep(svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, true, true>);
   }
   static void prepare_s3() { prep(svi::k_sweep_ring<G, V, R, T, MINB, Sweep::S3, false, false>); }
-  static void phi(const Params &P, cudaStream_t st, bool sparse, bool comm, uint32_t s0, uint32_t s1, uint32_t pub) {
-    if (s1 <= s0) return;
-    const uint32_t blocks = (uint32_t)(((uint64_t)(s1 - s0) * G + T - 1) / T);
-    if (sparse && comm) svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, true, true><<<blocks, T, kSmem, st>>>(P, s0, s1, pub);
-    else if (sparse) svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, true, false><<<blocks, T, kSmem, st>>>(P, s0, s1, pub);
-    else if (comm) svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, false, true><<<blocks, T, kSmem, st>>>(P, s0, s1, pub);
-    else svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, false, false><<<blocks, T, kSmem, st>>>(P, s0, s1, pub);
+  static void phi(const Params &P, cudaStream_t st, bool sparse, bool comm, uint32_t s0, uint32_t s1, uint32_t t0,
+                  uint32_t t1, uint32_t pub) {
+    const uint64_t cnt = (uint64_t)(s1 - s0) + (t1 - t0);
+    if (!cnt) return;
+    const uint32_t blocks = (uint32_t)((cnt * G + T - 1) / T);
+    if (sparse && comm) svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, true, true><<<blocks, T, kSmem, st>>>(P, s0, s1, t0, t1, pub);
+    else if (sparse) svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, true, false><<<blocks, T, kSmem, st>>>(P, s0, s1, t0, t1, pub);
+    else if (comm) svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, false, true><<<blocks, T, kSmem, st>>>(P, s0, s1, t0, t1, pub);
+    else svi::k_sweep_ring<G, V, R, T, MINB, Sweep::Phi, false, false><<<blocks, T, kSmem, st>>>(P, s0, s1, t0, t1, pub);
   }
   static void s3(const Params &P, cudaStream_t st, uint32_t blocks) {
     if (P.nseg <= P.nseg_lo) return;
-    svi::k_sweep_ring<G, V, R, T, MINB, Sweep::S3, false, false><<<blocks, T, kSmem, st>>>(P, P.nseg_lo, P.nseg, 0u);
+    svi::k_sweep_ring<G, V, R, T, MINB, Sweep::S3, false, false><<<blocks, T, kSmem, st>>>(P, P.nseg_lo, P.nseg, 0u, 0u, 0u);
   }
   static int max_blocks_s3(int sms, uint32_t) {
     auto kern = svi::k_sweep_ring<G, V, R, T, MINB, Sweep::S3, false, false>;
@@ -359,14 +364,22 @@ struct svi_ls {
   bool mg = false, mg_ipc = false, share_gamma = false;
   std::vector<uint32_t> bounds;          // node blocks of all shards
   std::vector<uint32_t> chunk_nodes;     // the own block cut into pipeline chunks: chunk c = [chunk_nodes[c], chunk_nodes[c+1])
-  cudaStream_t side = nullptr, own_main = nullptr;
+  cudaStream_t side = nullptr, own_main = nullptr, aux = nullptr;   // aux: the node passes of the chunk pipeline
+  cudaEvent_t ev_phi = nullptr, ev_node = nullptr;
   cudaEvent_t ev_chunk = nullptr, ev_refresh = nullptr, ev_side = nullptr;
+  // how rows travel to the peers: 0 = one copy-engine transfer per peer on the side stream, 1 = the same transfers
+  // fanned out over one stream per peer, 2 = a small SM kernel (reads a row once, stores it to every peer)
+  int push_mode = 2;
+  uint32_t push_blocks = 32;
+  cudaStream_t fan[svi::kMaxWorld] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[svi::kMaxWorld] = {};
   uint32_t epoch = 0, gamma_epoch = 0;
   uint32_t *d_mg_err = nullptr;
   // optional per-phase timing of svi_ls_mg_step (svi_ls_mg_timing): events on the main stream, ring of steps
-  static constexpr int kTimedSteps = 32, kMarks = 9;
+  static constexpr int kTimedSteps = 32, kMarks = 9, kSideMarks = 4;
   bool timing = false;
   cudaEvent_t tev[kTimedSteps][kMarks] = {};
+  cudaEvent_t sev[kTimedSteps][kSideMarks] = {};   // side stream: first mphi push .. M flag, first b push .. B flag
   uint32_t tsteps = 0;
   uint64_t mg_timeout_ns = 20ull * 1000000000ull;
 };
@@ -398,9 +411,20 @@ void free_all(svi_ls *h) {
   for (auto &row : h->tev)
     for (cudaEvent_t ev : row)
       if (ev) cudaEventDestroy(ev);
+  for (auto &row : h->sev)
+    for (cudaEvent_t ev : row)
+      if (ev) cudaEventDestroy(ev);
+  for (cudaStream_t st : h->fan)
+    if (st) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : h->ev_join)
+    if (ev) cudaEventDestroy(ev);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_chunk) cudaEventDestroy(h->ev_chunk);
   if (h->ev_refresh) cudaEventDestroy(h->ev_refresh);
   if (h->ev_side) cudaEventDestroy(h->ev_side);
+  if (h->ev_phi) cudaEventDestroy(h->ev_phi);
+  if (h->ev_node) cudaEventDestroy(h->ev_node);
+  if (h->aux) cudaStreamDestroy(h->aux);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->own_main) cudaStreamDestroy(h->own_main);
 }
@@ -617,6 +641,7 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   touch(svi::k_reduce_kpart); touch(svi::k_scale); touch(svi::k_partition); touch(svi::k_fill);
   touch(svi::k_pad_rows); touch(svi::k_unpad_rows);
   touch(svi::k_mg_signal); touch(svi::k_mg_wait); touch(svi::k_mg_kx_push); touch(svi::k_mg_kx_sum);
+  touch(svi::k_mg_push<uint4>); touch(svi::k_mg_push<uint32_t>);
   h->kpart_blocks = std::max(h->blocks_node, h->blocks_s3);
   const size_t cap = std::max(2 * (size_t)ops.lanes * ops.vec, 2 * (size_t)ops.s3_lanes * ops.s3_vec);
   cudaError_t e = cudaSuccess;
@@ -819,19 +844,16 @@ void launch_phi(svi_ls *h, cudaStream_t st, uint32_t iter, int write_comm, uint3
   const Params &P = h->P;
   auto phi = h->ops.phi_ring ? h->ops.phi_ring : h->ops.phi;
   const bool sparse = iter > 1000 && P.k_div10 > 0;
-  const bool whole = lo0 == 0 && lo1 == P.nseg_lo && up0 == P.nseg_lo && up1 == P.nseg;
   if (!write_comm) {
-    if (whole) phi(P, st, sparse, false, 0, P.nseg, 0);
-    else { phi(P, st, sparse, false, lo0, lo1, 0); phi(P, st, sparse, false, up0, up1, 0); }
+    phi(P, st, sparse, false, lo0, lo1, up0, up1, 0);
   } else if (h->shard) {
     // a shard holds the membership words of its own nodes only: the arg-max is taken on both sides of a link
-    if (whole) phi(P, st, sparse, true, 0, P.nseg, 0);
-    else { phi(P, st, sparse, true, lo0, lo1, 0); phi(P, st, sparse, true, up0, up1, 0); }
+    phi(P, st, sparse, true, lo0, lo1, up0, up1, 0);
   } else {
     // one arg-max per LINK (src/linksampling.cc:704-717 sets fmap[p] and fmap[q] from one max_k): the owner's side
     // computes it and publishes both endpoints' bits; the other side runs without the tally
-    phi(P, st, sparse, false, lo0, lo1, 0);
-    phi(P, st, sparse, true, up0, up1, 1);
+    phi(P, st, sparse, false, lo0, lo1, 0, 0, 0);
+    phi(P, st, sparse, true, up0, up1, 0, 0, 1);
   }
 }
 
@@ -970,7 +992,28 @@ static int mg_finish_attach(svi_ls *h, uint32_t world, uint32_t rank, const uint
     CK(cudaStreamCreateWithFlags(&h->own_main, cudaStreamNonBlocking));
     h->stream = h->own_main;
   }
-  if (!h->side) CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  if (!h->side) {   // highest priority: its few push blocks / flag kernels must not queue behind a whole sweep
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+  }
+  if (!h->aux) {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&h->ev_phi, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_node, cudaEventDisableTiming));
+  }
+  if (const char *pm = getenv("SVI_LS_MG_PUSH")) h->push_mode = !strcmp(pm, "ce") ? 0 : !strcmp(pm, "ce_multi") ? 1 : 2;
+  if (const char *pb = getenv("SVI_LS_MG_PUSH_BLOCKS")) h->push_blocks = (uint32_t)std::max(1, atoi(pb));
+  if (h->push_mode == 1 && !h->ev_fork) {
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (uint32_t r = 0; r < world; ++r) {
+      if (r == rank) continue;
+      CK(cudaStreamCreateWithFlags(&h->fan[r], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&h->ev_join[r], cudaEventDisableTiming));
+    }
+  }
   if (!h->ev_chunk) CK(cudaEventCreateWithFlags(&h->ev_chunk, cudaEventDisableTiming));
   if (!h->ev_refresh) CK(cudaEventCreateWithFlags(&h->ev_refresh, cudaEventDisableTiming));
   if (!h->ev_side) CK(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
@@ -981,8 +1024,17 @@ static int mg_finish_attach(svi_ls *h, uint32_t world, uint32_t rank, const uint
   if (world == 1) c = 1;
   h->chunk_nodes.assign(1, h->P.node_begin);
   const uint64_t total = h->he_prefix[h->nlocal];
+  // geometrically shrinking chunks (ratio q): what stays exposed is the LAST chunk's push
+  const char *qe = getenv("SVI_LS_MG_CHUNK_RATIO");
+  const double q = qe && atof(qe) > 0 ? atof(qe) : 0.7;
+  double wsum = 0, w = 1;
+  for (uint32_t i = 0; i < c; ++i, w *= q) wsum += w;
+  double acc = 0;
+  w = 1;
   for (uint32_t i = 1; i < c; ++i) {
-    const uint64_t target = total * i / c;
+    acc += w / wsum;
+    w *= q;
+    const uint64_t target = (uint64_t)((double)total * acc);
     uint32_t v = (uint32_t)(std::lower_bound(h->he_prefix.begin(), h->he_prefix.end(), target) - h->he_prefix.begin());
     v = std::min(v, h->nlocal);
     h->chunk_nodes.push_back(std::max(h->chunk_nodes.back(), h->P.node_begin + v));
@@ -1056,9 +1108,29 @@ int svi_ls_mg_share_gamma(svi_ls *h, int on) {
 static int mg_push_rows(svi_ls *h, cudaStream_t st, size_t off, size_t row_bytes, uint32_t v0, uint32_t v1) {
   if (v1 <= v0) return SVI_OK;
   const size_t at = off + (size_t)v0 * row_bytes, bytes = (size_t)(v1 - v0) * row_bytes;
+  if (h->push_mode == 2) {
+    if (at % 16 == 0 && bytes % 16 == 0) {
+      const size_t cnt = bytes / 16;
+      const uint32_t blocks = (uint32_t)std::min<size_t>(h->push_blocks, (cnt + 255) / 256);
+      svi::k_mg_push<uint4><<<blocks, 256, 0, st>>>(h->peers, at, cnt);
+    } else {
+      const size_t cnt = bytes / 4;
+      const uint32_t blocks = (uint32_t)std::min<size_t>(h->push_blocks, (cnt + 255) / 256);
+      svi::k_mg_push<uint32_t><<<blocks, 256, 0, st>>>(h->peers, at, cnt);
+    }
+    return SVI_OK;
+  }
+  if (h->push_mode == 1) CK(cudaEventRecord(h->ev_fork, st));
   for (uint32_t d = 1; d < h->peers.world; ++d) {
     const uint32_t r = (h->peers.rank + d) % h->peers.world;
-    CK(cudaMemcpyAsync(h->peers.arena[r] + at, h->d_arena + at, bytes, cudaMemcpyDeviceToDevice, st));
+    if (h->push_mode == 1) {
+      CK(cudaStreamWaitEvent(h->fan[r], h->ev_fork, 0));
+      CK(cudaMemcpyAsync(h->peers.arena[r] + at, h->d_arena + at, bytes, cudaMemcpyDeviceToDevice, h->fan[r]));
+      CK(cudaEventRecord(h->ev_join[r], h->fan[r]));
+      CK(cudaStreamWaitEvent(st, h->ev_join[r], 0));
+    } else {
+      CK(cudaMemcpyAsync(h->peers.arena[r] + at, h->d_arena + at, bytes, cudaMemcpyDeviceToDevice, st));
+    }
   }
   return SVI_OK;
 }
@@ -1073,8 +1145,10 @@ int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
   const uint32_t e = ++h->epoch, par = e & 1u, ld = P.ld;
   const bool multi = pr.world > 1;
   int rc;
+  cudaEvent_t *sev = h->timing ? h->sev[h->tsteps % svi_ls::kTimedSteps] : nullptr;
   cudaEvent_t *tev = h->timing ? h->tev[h->tsteps++ % svi_ls::kTimedSteps] : nullptr;
   auto mark = [&](int i) { if (tev) cudaEventRecord(tev[i], mn); };
+  auto smark = [&](int i) { if (sev && multi) cudaEventRecord(sev[i], side); };
   mark(0);
   // the peers' rows for this iteration (b, converged, ...) were pushed during their previous refresh
   if (multi && e > 1) svi::k_mg_wait<<<1, 32, 0, mn>>>(pr, svi::FLAG_B, e - 1, h->d_mg_err, h->mg_timeout_ns);
@@ -1086,14 +1160,25 @@ int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
   for (uint32_t c = 0; c < nchunks; ++c) {
     const uint32_t v0 = h->chunk_nodes[c], v1 = h->chunk_nodes[c + 1];
     launch_phi(h, mn, iter, write_comm, h->nlo[v0 - nb], h->nlo[v1 - nb], h->nup[v0 - nb], h->nup[v1 - nb]);
-    launch_node(h, mn, v0, v1, c);
-    if (multi) {
+    if (nchunks == 1) {
+      launch_node(h, mn, v0, v1, c);
       CK(cudaEventRecord(h->ev_chunk, mn));
+    } else {
+      // the chunk's node pass runs on the auxiliary stream, beside the next chunk's sweep (no bubble on the main one)
+      CK(cudaEventRecord(h->ev_phi, mn));
+      CK(cudaStreamWaitEvent(h->aux, h->ev_phi, 0));
+      launch_node(h, h->aux, v0, v1, c);
+      CK(cudaEventRecord(h->ev_chunk, h->aux));
+    }
+    if (multi) {
       CK(cudaStreamWaitEvent(side, h->ev_chunk, 0));
+      if (c == 0) smark(0);
       if ((rc = mg_push_rows(h, side, h->lay.mphi, (size_t)ld * 8, v0, v1))) return rc;
     }
   }
+  if (nchunks > 1) CK(cudaStreamWaitEvent(mn, h->ev_chunk, 0));   // all node passes are in (the aux stream is in order)
   if (multi) svi::k_mg_signal<<<1, 32, 0, side>>>(pr, svi::FLAG_M, e);
+  smark(1);
   mark(2);
   svi::k_reduce_kpart<<<4, 256, 0, mn>>>(h->d_kpart, nchunks * h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec, h->d_kvec, ld);
   if (multi) {   // all-reduce of sum, s1, s2 (`sum` feeds the annealing rescale, :541-542)
@@ -1110,6 +1195,7 @@ int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
     CK(cudaEventRecord(h->ev_refresh, mn));
     CK(cudaStreamWaitEvent(side, h->ev_refresh, 0));
     const uint32_t v0 = P.node_begin, v1 = P.node_end;
+    smark(2);
     if ((rc = mg_push_rows(h, side, h->lay.b, (size_t)ld * 8, v0, v1))) return rc;
     if ((rc = mg_push_rows(h, side, h->lay.conv[h->cur ^ 1], 4, v0, v1))) return rc;
     if (iter >= 1000) {   // the active-set branch (iter > 1000, :634) reads the neighbours' counts and masks
@@ -1118,6 +1204,7 @@ int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
     }
     if (h->share_gamma && (rc = mg_push_rows(h, side, h->lay.gamma, (size_t)ld * 8, v0, v1))) return rc;
     svi::k_mg_signal<<<1, 32, 0, side>>>(pr, svi::FLAG_B, e);
+    smark(3);
     svi::k_mg_wait<<<1, 32, 0, mn>>>(pr, svi::FLAG_M, e, h->d_mg_err, h->mg_timeout_ns);
   }
   mark(5);
@@ -1146,19 +1233,30 @@ int svi_ls_mg_timing(svi_ls *h, int enable, double *phase_ms, uint32_t *steps) {
   if (phase_ms) {   // mean over the recorded steps (at most the last kTimedSteps), then reset
     CK(cudaStreamSynchronize(h->stream));
     const uint32_t cnt = std::min<uint32_t>(h->tsteps, svi_ls::kTimedSteps);
-    for (int i = 0; i < svi_ls::kMarks - 1; ++i) phase_ms[i] = 0.0;
-    for (uint32_t s = 0; s < cnt; ++s)
+    if (h->side) CK(cudaStreamSynchronize(h->side));
+    for (int i = 0; i < svi_ls::kMarks + 1; ++i) phase_ms[i] = 0.0;
+    for (uint32_t s = 0; s < cnt; ++s) {
       for (int i = 0; i < svi_ls::kMarks - 1; ++i) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, h->tev[s][i], h->tev[s][i + 1]));
         phase_ms[i] += ms / cnt;
       }
+      if (h->peers.world > 1)
+        for (int i = 0; i < 2; ++i) {   // side stream: span of the mphi pushes, span of the b / converged / gamma pushes
+          float ms = 0.f;
+          CK(cudaEventElapsedTime(&ms, h->sev[s][2 * i], h->sev[s][2 * i + 1]));
+          phase_ms[svi_ls::kMarks - 1 + i] += ms / cnt;
+        }
+    }
     if (steps) *steps = cnt;
     h->tsteps = 0;
   }
-  if (enable && !h->tev[0][0])
+  if (enable && !h->tev[0][0]) {
     for (auto &row : h->tev)
       for (cudaEvent_t &ev : row) CK(cudaEventCreate(&ev));
+    for (auto &row : h->sev)
+      for (cudaEvent_t &ev : row) CK(cudaEventCreate(&ev));
+  }
   h->timing = enable != 0;
   h->tsteps = 0;
   return SVI_OK;

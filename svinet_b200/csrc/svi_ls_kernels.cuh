@@ -119,12 +119,14 @@ __device__ __forceinline__ double digamma_pos(double x) {
 // Output: part[seg] = sum of phi over the segment's neighbours (a K-row).
 template <int G, int V, bool LOGDOM, bool SPARSE, bool COMM>
 __global__ void __launch_bounds__(256) k_phi(const Params P, const uint32_t seg_first, const uint32_t seg_end,
-                                             const uint32_t publish) {
+                                             const uint32_t seg_first2, const uint32_t seg_end2, const uint32_t publish) {
   constexpr int U = (V <= 4) ? 2 : 1;   // neighbour rows in flight per group
   const unsigned mask = group_mask<G>();
   const uint32_t lane = threadIdx.x & (G - 1);
-  const uint32_t seg = seg_first + (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  if (seg >= seg_end) return;
+  // two ranges of the segment table in one launch (a chunk of nodes: its "lo" segments and its "up" segments)
+  const uint32_t sidx = (blockIdx.x * blockDim.x + threadIdx.x) / G, nseg1 = seg_end - seg_first;
+  if (sidx >= nseg1 + (seg_end2 - seg_first2)) return;
+  const uint32_t seg = sidx < nseg1 ? seg_first + sidx : seg_first2 + (sidx - nseg1);
   const uint32_t p = P.seg_node[seg], beg = P.seg_beg[seg], cnt = P.seg_cnt[seg];
   const uint32_t pc = P.conv[p];
   const uint32_t pa = SPARSE ? P.active[p] : 0u;

@@ -71,6 +71,22 @@ static __global__ void k_mg_wait(const Peers pr, const uint32_t kind, const uint
   mg_wait_flags(pr, kind, epoch, err, timeout_ns);
 }
 
+// Row push by the SMs: every 16-byte piece of [off, off + bytes) of OUR arena is read once and stored into the same
+// place of every peer's arena (posted NVLink writes).  A few small blocks on a high-priority stream: they slip onto
+// the SMs as sweep blocks retire.  (The alternative is one copy-engine transfer per peer, see svi_ls.cu.)
+template <class T>
+static __global__ void __launch_bounds__(256) k_mg_push(const Peers pr, const size_t off, const size_t count) {
+  const T *src = reinterpret_cast<const T *>(pr.arena[pr.rank] + off);
+  T *dst[kMaxWorld];
+  uint32_t nd = 0;
+  for (uint32_t d = 1; d < pr.world; ++d) dst[nd++] = reinterpret_cast<T *>(pr.arena[(pr.rank + d) % pr.world] + off);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    const T v = __ldcs(src + i);
+    for (uint32_t d = 0; d < nd; ++d) dst[d][i] = v;
+  }
+  __threadfence_system();
+}
+
 // all-reduce, first half: our `count` doubles (count <= kx_stride) go into slot [parity][which][rank] of every
 // shard's arena (our own included), then the flag `kind` is raised.  One block.
 static __global__ void k_mg_kx_push(const Peers pr, const double *src, const uint32_t count, const uint32_t parity,

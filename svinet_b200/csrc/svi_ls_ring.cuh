@@ -189,6 +189,7 @@ __device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_
 //   the s3-owner's side only, src/linksampling.cc:704-717 sets fmap[p] and fmap[q] from one max_k)
 template <int G, int V, int R, int T, int MINB, Sweep MODE, bool SPARSE, bool COMM>
 __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P, const uint32_t seg_first, const uint32_t seg_end,
+                                                        const uint32_t seg_first2, const uint32_t seg_end2,
                                                         const uint32_t publish) {
   static_assert(R <= G && (R & (R - 1)) == 0, "ring depth: power of two, at most one chunk");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -218,7 +219,8 @@ __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P, const ui
   __syncthreads();
 
   const double *src_rows = MODE == Sweep::Phi ? P.b : P.mphi;
-  const uint32_t nseg = seg_end - seg_first;
+  // two ranges of the segment table in one launch (a chunk of nodes: its "lo" segments and its "up" segments)
+  const uint32_t nseg1 = seg_end - seg_first, nseg = nseg1 + (seg_end2 - seg_first2);
 
   double2 s3acc[V];  // S3 only: per-lane column sums across this group's segments
 #pragma unroll
@@ -229,8 +231,9 @@ __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P, const ui
   // Phi: one segment per group (grid covers nseg).  S3: persistent, grid-stride over segments.
   const uint32_t warp_first = ggid - grp % (32 / G);   // first group id of this warp
   for (uint32_t base = warp_first; base < nseg; base += ngroups) {
-    const bool have = base + grp % (32 / G) < nseg;
-    const uint32_t seg = seg_first + base + grp % (32 / G);
+    const uint32_t sidx = base + grp % (32 / G);
+    const bool have = sidx < nseg;
+    const uint32_t seg = sidx < nseg1 ? seg_first + sidx : seg_first2 + (sidx - nseg1);
     const uint32_t p = have ? P.seg_node[seg] : 0u;
     const uint32_t beg = have ? P.seg_beg[seg] : 0u;
     const uint32_t cnt = have ? P.seg_cnt[seg] : 0u;

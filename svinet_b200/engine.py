@@ -244,14 +244,14 @@ class LinkSamplingEngine:
         _check(self.L, self.L.svi_ls_mg_share_gamma(self.h, int(on)))
 
     MG_PHASES = ("wait_b_rows", "phi+node", "allreduce_sum_s1_s2", "refresh", "wait_mphi_rows", "s3", "allreduce_s3+lambda",
-                 "drain_own_pushes")
+                 "drain_own_pushes", "side_mphi_pushes_span", "side_b_pushes_span")
 
     def mg_timing(self, enable=True, read=False):
         """enable/disable per-phase timing of mg_step; read=True returns {phase: mean ms} over the recorded steps"""
         if not read:
             _check(self.L, self.L.svi_ls_mg_timing(self.h, int(enable), None, None))
             return None
-        ms = np.zeros(8, dtype=np.float64)
+        ms = np.zeros(10, dtype=np.float64)
         cnt = C.c_uint32()
         _check(self.L, self.L.svi_ls_mg_timing(self.h, int(enable), _ptr(ms), C.byref(cnt)))
         return dict(zip(self.MG_PHASES, [float(x) for x in ms])), cnt.value

@@ -71,7 +71,7 @@ def test_cli_gpus_n_writes_the_reference_directory(cli, case, gpus):
     is src/main.cc:337-341) against the same reference fixtures as the single-GPU run.  On a one-GPU box the shards
     share the device (SVINET_SHARDS_ON_ONE_GPU=1): same code path, copies stay on the GPU."""
     import torch
-    env = {} if torch.cuda.device_count() >= gpus else {"SVINET_SHARDS_ON_ONE_GPU": "1"}
+    env = {} if torch.cuda.device_count() >= gpus else {"SVINET_SHARDS_ON_ONE_GPU": "1", "CUDA_DEVICE_MAX_CONNECTIONS": "32"}
     with Scratch() as d:
         ent, out = run_case(cli, case, d, extra=["-gpus", str(gpus)], env=env)
         flips = {}
