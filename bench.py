@@ -356,9 +356,6 @@ def run_ours(args):
             "what": "svi_ls_set_state(pinned host) + svi_ls_step + svi_ls_heldout + svi_ls_get_state(pinned host)"}
         del pin_g, pin_l
     else:
-        if peer:
-            eng.mg_share_gamma(True)     # the held-out pairs touch rows of every shard
-            runner.share_gamma = True
         e2e_steps = max(1, min(args.steps, 10))
         e2e = runner.e2e(step_fn=lambda i: runner.step(i, True, True), it0=it, steps=e2e_steps, nlinks=nlinks, unit=UNIT,
                          heldout=heldout_pairs(n, links, max(2, min(nlinks // 100, 2_000_000))))
@@ -371,13 +368,13 @@ def run_ours(args):
             verify = verify_sampled_rows(lambda: eng.step(it, False, True), eng.get_state,
                                          lambda: eng.get_converged()[0], n, k, links, 1.0 / k)
         else:
-            # collective: every rank steps; the whole gamma is on every rank (shared rows), rank 0 does the arithmetic
+            # collective: every rank steps and publishes its gamma rows; rank 0 does the arithmetic
             def all_step():
                 runner.step(it, False, True)
                 eng.sync()
                 dist.barrier()
-            verify = verify_sampled_rows(all_step, eng.get_state, lambda: eng.get_converged()[0], n, k, links, 1.0 / k,
-                                         compute=(rank == 0))
+            verify = verify_sampled_rows(all_step, runner.gather_state, lambda: eng.get_converged()[0], n, k, links,
+                                         1.0 / k, compute=(rank == 0))
         if verify is not None:
             verify["seconds"] = time.time() - t0
         it += 1
@@ -396,7 +393,7 @@ def run_ours(args):
             for i in range(args.checksum):
                 runner.step(i, True, i > 0)
             eng.sync(); dist.barrier()
-        g, lam = eng.get_state() if (world == 1 or peer) else runner.gather_state()
+        g, lam = eng.get_state() if world == 1 else runner.gather_state()
         cv = eng.get_converged()[0]
         checksum = {"steps": args.checksum, "gamma_sum": float(g.sum()), "gamma_sq_sum": float((g * g).sum()),
                     "lambda_sum": float(lam.sum()), "converged_nodes": int((cv != 0).sum()),

@@ -166,6 +166,10 @@ int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm);
 /* also push the refreshed gamma rows, so that every shard holds the whole gamma (svi_ls_heldout on any pair,
  * svi_ls_get_state of the whole matrix) */
 int svi_ls_mg_share_gamma(svi_ls *h, int on);
+/* Without replication: svi_ls_heldout reads the rows of other shards straight from their arenas (peer loads), and
+ * the whole gamma is assembled on demand -- every shard calls svi_ls_mg_publish_gamma (pushes its rows to all
+ * peers, asynchronous), after which svi_ls_get_state on any shard returns the whole matrix. */
+int svi_ls_mg_publish_gamma(svi_ls *h);
 int svi_ls_mg_error(svi_ls *h);
 /* Per-phase device times of svi_ls_mg_step, measured with events on the handle's stream: enable, run steps, then
  * read the mean over the (at most 32) last steps into phase_ms[10]:

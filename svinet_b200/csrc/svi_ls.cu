@@ -57,7 +57,7 @@ struct Ops {
   void (*lambda)(const Params &, cudaStream_t, int annealing, int update);
   void (*refresh)(const Params &, cudaStream_t, bool from_gacc);
   void (*heldout)(const Params &, cudaStream_t, uint64_t, const uint32_t *, const uint32_t *, const uint8_t *,
-                  double, double *);
+                  double, double *, const svi::Peers *peer_rows);
   int (*max_blocks_node)(int sms);
   int (*max_blocks_s3)(int sms);
   int lanes, vec, logdom;
@@ -117,10 +117,11 @@ struct Tile {
     else svi::k_refresh<G, V, L, false><<<blocks, kThreads, 0, st>>>(P);
   }
   static void heldout(const Params &P, cudaStream_t st, uint64_t np, const uint32_t *p, const uint32_t *q,
-                      const uint8_t *y, double eps, double *out) {
+                      const uint8_t *y, double eps, double *out, const svi::Peers *peer_rows) {
     if (!np) return;
     const uint32_t blocks = (uint32_t)((np * G + kThreads - 1) / kThreads);
-    svi::k_heldout<G, V><<<blocks, kThreads, 0, st>>>(P, np, p, q, y, eps, out);
+    if (peer_rows) svi::k_heldout<G, V, svi::Peers><<<blocks, kThreads, 0, st>>>(P, *peer_rows, np, p, q, y, eps, out);
+    else svi::k_heldout<G, V, svi::LocalRows><<<blocks, kThreads, 0, st>>>(P, svi::LocalRows{P.gamma}, np, p, q, y, eps, out);
   }
   static int occ(const void *fn, int sms) {
     int per_sm = 0;
@@ -141,7 +142,8 @@ struct Tile {
     touch(svi::k_lambda<L>);
     touch(svi::k_refresh<G, V, L, true>);
     touch(svi::k_refresh<G, V, L, false>);
-    touch(svi::k_heldout<G, V>);
+    touch(svi::k_heldout<G, V, svi::LocalRows>);
+    touch(svi::k_heldout<G, V, svi::Peers>);
   }
   static Ops ops() {
     Ops o{phi, node, s3, lambda, refresh, heldout, max_blocks_node, max_blocks_s3, G, V, L ? 1 : 0};
@@ -364,16 +366,17 @@ struct svi_ls {
   bool mg = false, mg_ipc = false, share_gamma = false;
   std::vector<uint32_t> bounds;          // node blocks of all shards
   std::vector<uint32_t> chunk_nodes;     // the own block cut into pipeline chunks: chunk c = [chunk_nodes[c], chunk_nodes[c+1])
-  cudaStream_t side = nullptr, own_main = nullptr, aux = nullptr;   // aux: the node passes of the chunk pipeline
-  cudaEvent_t ev_phi = nullptr, ev_node = nullptr;
+  cudaStream_t side = nullptr, own_main = nullptr, aux = nullptr, up = nullptr;   // aux: node passes, up: "up" segments
+  cudaEvent_t ev_phi = nullptr, ev_node = nullptr, ev_up = nullptr;
   cudaEvent_t ev_chunk = nullptr, ev_refresh = nullptr, ev_side = nullptr;
   // how rows travel to the peers: 0 = one copy-engine transfer per peer on the side stream, 1 = the same transfers
   // fanned out over one stream per peer, 2 = a small SM kernel (reads a row once, stores it to every peer)
-  int push_mode = 2;
+  int push_mode = 1;
   uint32_t push_blocks = 32;
   cudaStream_t fan[svi::kMaxWorld] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[svi::kMaxWorld] = {};
   uint32_t epoch = 0, gamma_epoch = 0;
+  bool gamma_wait = false;       // svi_ls_mg_publish_gamma ran: the next svi_ls_get_state awaits the peers' rows
   uint32_t *d_mg_err = nullptr;
   // optional per-phase timing of svi_ls_mg_step (svi_ls_mg_timing): events on the main stream, ring of steps
   static constexpr int kTimedSteps = 32, kMarks = 9, kSideMarks = 4;
@@ -424,6 +427,8 @@ void free_all(svi_ls *h) {
   if (h->ev_side) cudaEventDestroy(h->ev_side);
   if (h->ev_phi) cudaEventDestroy(h->ev_phi);
   if (h->ev_node) cudaEventDestroy(h->ev_node);
+  if (h->ev_up) cudaEventDestroy(h->ev_up);
+  if (h->up) cudaStreamDestroy(h->up);
   if (h->aux) cudaStreamDestroy(h->aux);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->own_main) cudaStreamDestroy(h->own_main);
@@ -641,7 +646,7 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   touch(svi::k_reduce_kpart); touch(svi::k_scale); touch(svi::k_partition); touch(svi::k_fill);
   touch(svi::k_pad_rows); touch(svi::k_unpad_rows);
   touch(svi::k_mg_signal); touch(svi::k_mg_wait); touch(svi::k_mg_kx_push); touch(svi::k_mg_kx_sum);
-  touch(svi::k_mg_push<uint4>); touch(svi::k_mg_push<uint32_t>);
+  touch(svi::k_mg_or_rows); touch(svi::k_mg_push<uint4>); touch(svi::k_mg_push<uint32_t>);
   h->kpart_blocks = std::max(h->blocks_node, h->blocks_s3);
   const size_t cap = std::max(2 * (size_t)ops.lanes * ops.vec, 2 * (size_t)ops.s3_lanes * ops.s3_vec);
   cudaError_t e = cudaSuccess;
@@ -772,6 +777,10 @@ int svi_ls_get_state(svi_ls *h, double *gamma, double *lambda) {
   const Params &P = h->P;
   const size_t nk = (size_t)P.n * P.k;
   if (gamma && h->share_gamma) mg_await_rows(h);   // the other shards' rows of the last iteration
+  if (gamma && h->gamma_wait) {                     // ... or of svi_ls_mg_publish_gamma
+    svi::k_mg_wait<<<1, 32, 0, h->stream>>>(h->peers, svi::FLAG_G, h->gamma_epoch, h->d_mg_err, h->mg_timeout_ns);
+    h->gamma_wait = false;
+  }
   if (gamma) {
     if (P.ld == P.k) {
       CK(cudaMemcpyAsync(gamma, h->d_gamma, nk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -838,22 +847,27 @@ int begin_iteration(svi_ls *h, cudaStream_t st, int write_comm) {
   return SVI_OK;
 }
 
-// phi sweep over the "lo" segments [lo0, lo1) and the "up" segments [up0, up1)
-void launch_phi(svi_ls *h, cudaStream_t st, uint32_t iter, int write_comm, uint32_t lo0, uint32_t lo1, uint32_t up0,
-                uint32_t up1) {
+// phi sweep over the "lo" segments [lo0, lo1) (on stream st) and the "up" segments [up0, up1) (on stream st_up)
+void launch_phi(svi_ls *h, cudaStream_t st, cudaStream_t st_up, uint32_t iter, int write_comm, uint32_t lo0, uint32_t lo1,
+                uint32_t up0, uint32_t up1) {
   const Params &P = h->P;
   auto phi = h->ops.phi_ring ? h->ops.phi_ring : h->ops.phi;
   const bool sparse = iter > 1000 && P.k_div10 > 0;
   if (!write_comm) {
-    phi(P, st, sparse, false, lo0, lo1, up0, up1, 0);
-  } else if (h->shard) {
-    // a shard holds the membership words of its own nodes only: the arg-max is taken on both sides of a link
+    if (st == st_up) phi(P, st, sparse, false, lo0, lo1, up0, up1, 0);
+    else { phi(P, st, sparse, false, lo0, lo1, 0, 0, 0); phi(P, st_up, sparse, false, up0, up1, 0, 0, 0); }
+  } else if (h->shard && !h->mg) {
+    // a shard driven phase by phase (svi_ls_phase_*) holds the membership words of its own nodes only: the arg-max
+    // is taken on both sides of a link
     phi(P, st, sparse, true, lo0, lo1, up0, up1, 0);
   } else {
     // one arg-max per LINK (src/linksampling.cc:704-717 sets fmap[p] and fmap[q] from one max_k): the owner's side
-    // computes it and publishes both endpoints' bits; the other side runs without the tally
+    // computes it and sets both endpoints' bits; the "lo" segments run the kernel without the tally.  (Two launches:
+    // one launch with a per-warp switch measured 58.5 ms against 54.8 ms at config 4.)  svi_ls_mg_step: the bit of a
+    // neighbour owned by another shard lands in the local replica of the membership words and is merged after the
+    // sweep, k_mg_or_rows.
     phi(P, st, sparse, false, lo0, lo1, 0, 0, 0);
-    phi(P, st, sparse, true, up0, up1, 0, 0, 1);
+    phi(P, st_up, sparse, true, up0, up1, 0, 0, 1);
   }
 }
 
@@ -888,7 +902,7 @@ int svi_ls_phase_phi(svi_ls *h, uint32_t iter, int write_comm) {
   const Params &P = h->P;
   int rc = begin_iteration(h, h->stream, write_comm);
   if (rc) return rc;
-  launch_phi(h, h->stream, iter, write_comm, 0, P.nseg_lo, P.nseg_lo, P.nseg);
+  launch_phi(h, h->stream, h->stream, iter, write_comm, 0, P.nseg_lo, P.nseg_lo, P.nseg);
   CK(cudaGetLastError());
   return SVI_OK;
 }
@@ -977,6 +991,8 @@ int svi_ls_peer_export(svi_ls *h, void *blob, size_t blob_bytes) {
   return SVI_OK;
 }
 
+static int mg_push_rows(svi_ls *h, cudaStream_t st, size_t off, size_t row_bytes, uint32_t v0, uint32_t v1);
+
 static int mg_finish_attach(svi_ls *h, uint32_t world, uint32_t rank, const uint32_t *bounds, uint32_t chunks) {
   if (bounds[0] != 0 || bounds[world] != h->P.n || bounds[rank] != h->P.node_begin || bounds[rank + 1] != h->P.node_end)
     return fail(SVI_ERR_INVALID, "svi_ls_peer_attach: bounds do not match the handle's node block [%u,%u)", h->P.node_begin,
@@ -987,6 +1003,8 @@ static int mg_finish_attach(svi_ls *h, uint32_t world, uint32_t rank, const uint
   h->peers.arena[rank] = h->d_arena;
   h->peers.flags_off = h->lay.flags;
   h->peers.kx_off = h->lay.kx;
+  h->peers.gamma_off = h->lay.gamma;
+  for (uint32_t r = 0; r <= world; ++r) h->peers.bounds[r] = bounds[r];
   h->peers.kx_stride = 4 * h->P.ld;
   if (!h->stream) {   // the legacy default stream would serialise the shards of one process: own streams
     CK(cudaStreamCreateWithFlags(&h->own_main, cudaStreamNonBlocking));
@@ -1003,6 +1021,8 @@ static int mg_finish_attach(svi_ls *h, uint32_t world, uint32_t rank, const uint
     CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi));
     CK(cudaEventCreateWithFlags(&h->ev_phi, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_node, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&h->up, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming));
   }
   if (const char *pm = getenv("SVI_LS_MG_PUSH")) h->push_mode = !strcmp(pm, "ce") ? 0 : !strcmp(pm, "ce_multi") ? 1 : 2;
   if (const char *pb = getenv("SVI_LS_MG_PUSH_BLOCKS")) h->push_blocks = (uint32_t)std::max(1, atoi(pb));
@@ -1026,7 +1046,7 @@ static int mg_finish_attach(svi_ls *h, uint32_t world, uint32_t rank, const uint
   const uint64_t total = h->he_prefix[h->nlocal];
   // geometrically shrinking chunks (ratio q): what stays exposed is the LAST chunk's push
   const char *qe = getenv("SVI_LS_MG_CHUNK_RATIO");
-  const double q = qe && atof(qe) > 0 ? atof(qe) : 0.7;
+  const double q = qe && atof(qe) > 0 ? atof(qe) : 0.6;
   double wsum = 0, w = 1;
   for (uint32_t i = 0; i < c; ++i, w *= q) wsum += w;
   double acc = 0;
@@ -1098,6 +1118,21 @@ int svi_ls_peer_attach_local(svi_ls *h, uint32_t world, uint32_t rank, const uin
   return mg_finish_attach(h, world, rank, bounds, chunks);
 }
 
+int svi_ls_mg_publish_gamma(svi_ls *h) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  if (!h->mg) return fail(SVI_ERR_INVALID, "svi_ls_mg_publish_gamma: svi_ls_peer_attach[_local] first");
+  DeviceGuard guard(h->device);
+  ++h->gamma_epoch;
+  if (h->peers.world > 1) {
+    int rc = mg_push_rows(h, h->stream, h->lay.gamma, (size_t)h->P.ld * 8, h->P.node_begin, h->P.node_end);
+    if (rc) return rc;
+    svi::k_mg_signal<<<1, 32, 0, h->stream>>>(h->peers, svi::FLAG_G, h->gamma_epoch);
+    h->gamma_wait = true;
+  }
+  CK(cudaGetLastError());
+  return SVI_OK;
+}
+
 int svi_ls_mg_share_gamma(svi_ls *h, int on) {
   if (!h) return fail(SVI_ERR_INVALID, "null handle");
   h->share_gamma = on != 0;
@@ -1159,14 +1194,23 @@ int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
   const uint32_t nchunks = (uint32_t)h->chunk_nodes.size() - 1, nb = P.node_begin;
   for (uint32_t c = 0; c < nchunks; ++c) {
     const uint32_t v0 = h->chunk_nodes[c], v1 = h->chunk_nodes[c + 1];
-    launch_phi(h, mn, iter, write_comm, h->nlo[v0 - nb], h->nlo[v1 - nb], h->nup[v0 - nb], h->nup[v1 - nb]);
     if (nchunks == 1) {
+      launch_phi(h, mn, mn, iter, write_comm, h->nlo[v0 - nb], h->nlo[v1 - nb], h->nup[v0 - nb], h->nup[v1 - nb]);
       launch_node(h, mn, v0, v1, c);
       CK(cudaEventRecord(h->ev_chunk, mn));
     } else {
-      // the chunk's node pass runs on the auxiliary stream, beside the next chunk's sweep (no bubble on the main one)
+      // the chunk's "lo" segments on the main stream, its "up" segments on a second one: each stream's launch
+      // boundaries (a partial last wave) are filled by the other stream's blocks.  The chunk's node pass follows
+      // both on the auxiliary stream, beside the next chunk's sweep.
+      if (c == 0) {
+        CK(cudaEventRecord(h->ev_phi, mn));
+        CK(cudaStreamWaitEvent(h->up, h->ev_phi, 0));
+      }
+      launch_phi(h, mn, h->up, iter, write_comm, h->nlo[v0 - nb], h->nlo[v1 - nb], h->nup[v0 - nb], h->nup[v1 - nb]);
       CK(cudaEventRecord(h->ev_phi, mn));
       CK(cudaStreamWaitEvent(h->aux, h->ev_phi, 0));
+      CK(cudaEventRecord(h->ev_up, h->up));
+      CK(cudaStreamWaitEvent(h->aux, h->ev_up, 0));
       launch_node(h, h->aux, v0, v1, c);
       CK(cudaEventRecord(h->ev_chunk, h->aux));
     }
@@ -1184,6 +1228,10 @@ int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
   if (multi) {   // all-reduce of sum, s1, s2 (`sum` feeds the annealing rescale, :541-542)
     svi::k_mg_kx_push<<<1, 256, 0, mn>>>(pr, h->d_kvec, 3 * ld, par, 0, svi::FLAG_KXN, e);
     svi::k_mg_kx_sum<<<1, 256, 0, mn>>>(pr, h->d_kvec, 3 * ld, par, 0, svi::FLAG_KXN, e, h->d_mg_err, h->mg_timeout_ns);
+  }
+  if (multi && write_comm && P.nseg) {   // membership words of our rows: merge the peers' replicas (their sweeps are done)
+    const size_t first = (size_t)P.node_begin * P.words, cnt = (size_t)(P.node_end - P.node_begin) * P.words;
+    svi::k_mg_or_rows<<<(uint32_t)std::min<size_t>((cnt + 255) / 256, (size_t)h->sms * 2), 256, 0, mn>>>(pr, h->lay.mbits, first, cnt);
   }
   mark(3);
   // refresh BEFORE the s3 sweep (it needs `sum` only); its rows travel beside the sweep
@@ -1314,11 +1362,13 @@ int svi_ls_heldout(svi_ls *h, uint64_t npairs, const uint32_t *p, const uint32_t
   uint32_t *d_p = reinterpret_cast<uint32_t *>(d_out + npairs);
   uint32_t *d_q = d_p + npairs;
   uint8_t *d_y = reinterpret_cast<uint8_t *>(d_q + npairs);
+  // sharded: the rows of other shards are read from their arenas (peer loads), unless gamma is replicated
+  const bool peer_rows = h->mg && h->peers.world > 1 && !h->share_gamma;
   if (h->share_gamma) mg_await_rows(h);
   CK(cudaMemcpyAsync(d_p, p, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(d_q, q, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(d_y, y, npairs, cudaMemcpyHostToDevice, h->stream));
-  h->ops.heldout(h->P, h->stream, npairs, d_p, d_q, d_y, epsilon, d_out);
+  h->ops.heldout(h->P, h->stream, npairs, d_p, d_q, d_y, epsilon, d_out, peer_rows ? &h->peers : nullptr);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(loglik, d_out, npairs * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));

@@ -578,8 +578,14 @@ __global__ void __launch_bounds__(256) k_refresh(const Params P) {
 // The reference's non-link form is an O(K^2) double sum of pi_p[zp]*pi_q[zq]*(1 - rate(zp,zq))
 // with rate = beta_z on the diagonal and epsilon = 1e-30 off it; 1 - 1e-30 == 1 in FP64, so the
 // sum equals  sum_z pi_p[z] * (S_q - pi_q[z]*beta_z)  with S_q = sum_z pi_q[z]: O(K).
-template <int G, int V>
-__global__ void __launch_bounds__(256) k_heldout(const Params P, uint64_t npairs, const uint32_t *pp,
+// ROWS: where a node's gamma row lives -- LocalRows (the handle's own matrix) or svi::Peers (the arena of the shard
+// that owns the node, svi_ls_mg.cuh).
+struct LocalRows {
+  const double *gamma;
+  __device__ __forceinline__ const double *gamma_row(uint32_t node, uint32_t ld) const { return gamma + (size_t)node * ld; }
+};
+template <int G, int V, class ROWS>
+__global__ void __launch_bounds__(256) k_heldout(const Params P, const ROWS rows, uint64_t npairs, const uint32_t *pp,
                                                  const uint32_t *qq, const uint8_t *yy, double epsilon,
                                                  double *out) {
   const unsigned mask = group_mask<G>();
@@ -590,11 +596,12 @@ __global__ void __launch_bounds__(256) k_heldout(const Params P, uint64_t npairs
   const int y = yy[i];
   double2 gp[V], gq[V];
   double sp = 0.0, sq = 0.0;
+  const double *rp = rows.gamma_row(p, P.ld), *rq = rows.gamma_row(q, P.ld);
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     const uint32_t c0 = 2u * (lane + G * j);
-    gp[j] = ld_row2(P.gamma + (size_t)p * P.ld, c0, P.ld);
-    gq[j] = ld_row2(P.gamma + (size_t)q * P.ld, c0, P.ld);
+    gp[j] = ld_row2(rp, c0, P.ld);
+    gq[j] = ld_row2(rq, c0, P.ld);
     sp += gp[j].x + gp[j].y;
     sq += gq[j].x + gq[j].y;
   }

@@ -21,7 +21,15 @@ struct Peers {
   uint32_t world, rank;
   unsigned char *arena[kMaxWorld];   // arena base of every shard as mapped in THIS process (own arena included)
   uint64_t flags_off, kx_off;        // byte offsets of the flag table / K-vector slots inside an arena
+  uint64_t gamma_off;                // ... of the gamma matrix
   uint32_t kx_stride;                // doubles per K-vector slot (4 * ld)
+  uint32_t bounds[kMaxWorld + 1];    // node blocks of the shards
+  // the gamma row of `node` in the arena of the shard that owns it (a peer load over NVLink when it is not ours)
+  __device__ __forceinline__ const double *gamma_row(uint32_t node, uint32_t ld) const {
+    uint32_t r = 0;
+    while (r + 1 < world && node >= bounds[r + 1]) ++r;
+    return reinterpret_cast<const double *>(arena[r] + gamma_off) + (size_t)node * ld;
+  }
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
@@ -85,6 +93,19 @@ static __global__ void __launch_bounds__(256) k_mg_push(const Peers pr, const si
     for (uint32_t d = 0; d < nd; ++d) dst[d][i] = v;
   }
   __threadfence_system();
+}
+
+// Link-community membership words of OUR rows: OR of every shard's replica (a shard sets the bits of both endpoints of
+// the links it owns in its own replica, svi_ls_ring.cuh `publish`).  Peer loads, ~n * words * 4 / world bytes per peer.
+static __global__ void __launch_bounds__(256) k_mg_or_rows(const Peers pr, const size_t off, const size_t first,
+                                                           const size_t count) {
+  uint32_t *own = reinterpret_cast<uint32_t *>(pr.arena[pr.rank] + off) + first;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t v = own[i];
+    for (uint32_t d = 1; d < pr.world; ++d)
+      v |= __ldcg(reinterpret_cast<const uint32_t *>(pr.arena[(pr.rank + d) % pr.world] + off) + first + i);
+    own[i] = v;
+  }
 }
 
 // all-reduce, first half: our `count` doubles (count <= kx_stride) go into slot [parity][which][rank] of every

@@ -185,7 +185,7 @@ __device__ __forceinline__ void phi_row(const Params &P, uint32_t rbase, uint32_
 // first part and the one-hot shortcut links (:619-631) the second; for a converged p it is the other way round.
 // The ring loop runs over the full part only -- no per-neighbour flag load, no lock-stepped pass for a shortcut link
 // -- and the shortcut part is tallied G neighbours per instruction.
-//   publish (COMM only): the link-community bit is also set for the neighbour q (one arg-max per LINK, computed on
+//   publish (COMM only; launched over the "up" segments): the link-community bit is also set for the neighbour q (one arg-max per LINK, computed on
 //   the s3-owner's side only, src/linksampling.cc:704-717 sets fmap[p] and fmap[q] from one max_k)
 template <int G, int V, int R, int T, int MINB, Sweep MODE, bool SPARSE, bool COMM>
 __global__ void __launch_bounds__(T, MINB) k_sweep_ring(const Params P, const uint32_t seg_first, const uint32_t seg_end,

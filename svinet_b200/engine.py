@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "svi_ls_phase_node", "svi_ls_phase_s3", "svi_ls_phase_finish", "svi_ls_phase_refresh", "svi_ls_phase_lambda",
     "svi_ls_device_buffer",
     "svi_ls_peer_blob_bytes", "svi_ls_peer_export", "svi_ls_peer_attach", "svi_ls_peer_attach_local", "svi_ls_mg_step",
-    "svi_ls_mg_share_gamma", "svi_ls_mg_error", "svi_ls_mg_timing", "svi_ls_get_membership_rows",
+    "svi_ls_mg_share_gamma", "svi_ls_mg_publish_gamma", "svi_ls_mg_error", "svi_ls_mg_timing", "svi_ls_get_membership_rows",
     "svi_ls_get_info", "svi_ls_last_error", "svi_ls_abi_version",
 ]
 
@@ -85,6 +85,7 @@ def load_library(path=None):
     L.svi_ls_peer_attach_local.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32]
     L.svi_ls_mg_step.argtypes = [vp, C.c_uint32, C.c_int, C.c_int]
     L.svi_ls_mg_share_gamma.argtypes = [vp, C.c_int]
+    L.svi_ls_mg_publish_gamma.argtypes = [vp]
     L.svi_ls_mg_error.argtypes = [vp]
     L.svi_ls_mg_timing.argtypes = [vp, C.c_int, vp, vp]
     L.svi_ls_get_membership_rows.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
@@ -239,6 +240,9 @@ class LinkSamplingEngine:
 
     def mg_step(self, it, annealing, write_comm):
         _check(self.L, self.L.svi_ls_mg_step(self.h, it, int(annealing), int(write_comm)))
+
+    def mg_publish_gamma(self):
+        _check(self.L, self.L.svi_ls_mg_publish_gamma(self.h))
 
     def mg_share_gamma(self, on=True):
         _check(self.L, self.L.svi_ls_mg_share_gamma(self.h, int(on)))

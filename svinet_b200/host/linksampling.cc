@@ -224,7 +224,6 @@ void LinkSampling::create_device() {
   dev_ = devs_[0];
   for (uint32_t i = 0; i < g; ++i) {
     DEV(svi_ls_peer_attach_local(devs_[i], g, i, bounds_.data(), devs_.data(), 0));
-    DEV(svi_ls_mg_share_gamma(devs_[i], 1));   // shard 0 evaluates the held-out pairs and writes the model
   }
   for (uint32_t i = 0; i < g; ++i) DEV(svi_ls_set_state(devs_[i], gamma_.data(), lambda_.data()));
 }
@@ -427,7 +426,12 @@ void LinkSampling::assign_training_links() {
 
 bool LinkSampling::validation_likelihood() {
   if (env_.accuracy) return false;
-  DEV(svi_ls_heldout(dev_, hp_.size(), hp_.data(), hq_.data(), hy_.data(), env_.epsilon, hll_.data()));
+  // -gpus N: every shard evaluates a slice of the pairs (rows of other shards are peer loads inside the library)
+  const size_t ng = devs_.size(), np = hp_.size();
+  for (size_t i = 0; i < ng; ++i) {
+    const size_t a = np * i / ng, b = np * (i + 1) / ng;
+    DEV(svi_ls_heldout(devs_[i], b - a, hp_.data() + a, hq_.data() + a, hy_.data() + a, env_.epsilon, hll_.data() + a));
+  }
   uint32_t k = 0, kzeros = 0, kones = 0;
   double s = .0, szeros = 0, sones = 0;
   for (size_t i = 0; i < hll_.size(); ++i) {
@@ -481,7 +485,11 @@ void LinkSampling::test_likelihood_line() {
   fflush(tf_);
 }
 
-void LinkSampling::fetch_state() { DEV(svi_ls_get_state(dev_, gamma_.data(), lambda_.data())); }
+void LinkSampling::fetch_state() {
+  if (devs_.size() > 1)   // every shard sends its gamma rows to the others; shard 0 then holds the whole matrix
+    for (svi_ls *d : devs_) DEV(svi_ls_mg_publish_gamma(d));
+  DEV(svi_ls_get_state(dev_, gamma_.data(), lambda_.data()));
+}
 
 void LinkSampling::save_model() {
   FILE *gf = open_or_die(env_.file("/gamma.txt"), "w", "gamma");

@@ -280,7 +280,7 @@ class ShardedLinkSampling:
         """Full gamma [n,k] and lambda [k,2] on every rank (for save_model / parity checks)."""
         if self.exchange == "peer":
             if not self.share_gamma:
-                raise RuntimeError("gather_state over the peer exchange needs share_gamma=True")
+                self.eng.mg_publish_gamma()        # collective: every rank pushes its rows to every peer
             return self.eng.get_state()
         self._allgather_rows("gamma")
         return self.eng.get_state()
@@ -312,8 +312,8 @@ class ShardedLinkSampling:
                 step_fn(it)
                 it += 1
                 if self.exchange == "peer":
-                    # gamma rows were pushed by the step itself (share_gamma); only this rank's block of the
-                    # membership words is read back
+                    # held-out pairs: rows of other shards are peer loads inside svi_ls_heldout; only this rank's
+                    # block of the membership words is read back
                     ll = self.eng.heldout(hp, hq, hy)
                     nb, ne = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
                     bits = self.eng.membership_rows(nb, ne - nb)
@@ -328,7 +328,7 @@ class ShardedLinkSampling:
         return {"value": nlinks * steps / float(t.item()), "unit": unit, "steps": steps,
                 "h2d_bytes_per_step": int(hp.nbytes + hq.nbytes + hy.nbytes),
                 "d2h_bytes_per_step": int(ll.nbytes + bits.nbytes),
-                "what": ("per rank and iteration: svi_ls_mg_step (peer-memory exchanges, gamma rows shared) + "
+                "what": ("per rank and iteration: svi_ls_mg_step (peer-memory exchanges) + "
                          "svi_ls_heldout on 1/world of the pairs (host in/out) + svi_ls_get_membership_rows of the "
                          "rank's own block (host bits)") if self.exchange == "peer" else
                         ("per rank and iteration: sharded step (NCCL exchanges) + gamma row all-gather + "

@@ -20,14 +20,19 @@ from test_gpu_parity_ring import oracle_state
 pytestmark = pytest.mark.gpu
 
 
-def run_sharded_vs_oracle(n, k, links, gamma, conv, world, chunks, sched, seg_len=0):
+def run_sharded_vs_oracle(n, k, links, gamma, conv, world, chunks, sched, seg_len=0, share=True):
     st = oracle_state(n, k, links, gamma, np.ones((k, 2)), conv)
     bounds = plan_shards(n, links, world)
     engines = [LinkSamplingEngine(n, k, links, node_range=(int(bounds[r]), int(bounds[r + 1])), seg_len=seg_len)
                for r in range(world)]
     LinkSamplingEngine.attach_local(engines, bounds, chunks=chunks)
+    rng = np.random.default_rng(7)
+    hp = rng.integers(0, n, 300).astype(np.uint32)
+    hq = ((hp + 1 + rng.integers(0, n - 1, 300)) % n).astype(np.uint32)
+    hy = rng.integers(0, 2, 300).astype(np.uint8)
     for e in engines:
-        e.mg_share_gamma(True)
+        if share:
+            e.mg_share_gamma(True)
         e.set_state(st.arr("gamma"), st.arr("lambda_"))
         e.set_converged(st.arr("converged"))
     for it, ann, wc in sched:
@@ -36,6 +41,14 @@ def run_sharded_vs_oracle(n, k, links, gamma, conv, world, chunks, sched, seg_le
             e.mg_step(it, ann, wc)
         for e in engines:
             e.sync()
+        # held-out likelihood of arbitrary pairs on every shard: rows of other shards are replicated (share) or read
+        # from the owner's arena (peer loads)
+        want_ll = np.array([st.edge_likelihood(int(a), int(b), int(c)) for a, b, c in zip(hp, hq, hy)])
+        for e in engines:
+            assert rel_err(e.heldout(hp, hq, hy), want_ll, floor=1e-3) <= TOL
+        if not share:
+            for e in engines:
+                e.mg_publish_gamma()
         mem = np.zeros((n, k), dtype=np.uint8)
         for r, e in enumerate(engines):
             tag = "world=%d shard %d iter %d" % (world, r, it)
@@ -68,8 +81,8 @@ def run_sharded_vs_oracle(n, k, links, gamma, conv, world, chunks, sched, seg_le
     return shortcut
 
 
-@pytest.mark.parametrize("world,k,chunks", [(2, 12, 1), (2, 200, 4), (3, 100, 3), (4, 64, 2)])
-def test_shards_on_one_gpu_match_oracle(world, k, chunks):
+@pytest.mark.parametrize("world,k,chunks,share", [(2, 12, 1, True), (2, 200, 4, False), (3, 100, 3, False), (4, 64, 2, True)])
+def test_shards_on_one_gpu_match_oracle(world, k, chunks, share):
     n = 900
     links = synth.mmsb_links(n, k, 30 * n, seed=50 + k)
     gamma, _ = synth.random_state(n, k, links, seed=k)
@@ -78,7 +91,7 @@ def test_shards_on_one_gpu_match_oracle(world, k, chunks):
     who = rng.random(n) < 0.25
     conv[who] = rng.integers(1, k + 1, who.sum())
     sched = [(0, 1, 0), (1, 1, 1), (2, 0, 1), (3, 0, 0), (4, 1, 1)]
-    assert run_sharded_vs_oracle(n, k, links, gamma, conv, world, chunks, sched, seg_len=64) > 0
+    assert run_sharded_vs_oracle(n, k, links, gamma, conv, world, chunks, sched, seg_len=64, share=share) > 0
 
 
 def test_shards_where_nodes_converge_on_the_way():
@@ -92,4 +105,4 @@ def test_shards_where_nodes_converge_on_the_way():
         links, gamma = st.arr("links").copy(), st.arr("gamma").copy()
         m.close(); g.close()
     sched = [(it, it < 14, 1) for it in range(28)]
-    run_sharded_vs_oracle(75, 4, links, gamma, np.zeros(75, dtype=np.uint32), 3, 2, sched)
+    run_sharded_vs_oracle(75, 4, links, gamma, np.zeros(75, dtype=np.uint32), 3, 2, sched, share=False)
