@@ -278,23 +278,31 @@ def run_ours(args):
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
+        ev[s][0].record(stream)
         if world == 1:
-            ev[s][0].record(stream)
-            eng.phase_phi(it, it > 0); ev[s][1].record(stream)
-            eng.phase_node(); ev[s][2].record(stream)
-            eng.phase_s3(); ev[s][3].record(stream)
-            eng.phase_finish(True); ev[s][4].record(stream)
+            eng.step(it, True, it > 0)            # svi_ls_step: the iteration as one CUDA graph launch
         else:
-            ev[s][0].record(stream)
             runner.step(it, True, it > 0, events=ev[s])
-            ev[s][4].record(stream)
+        ev[s][4].record(stream)
         it += 1
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     total_ms = ev[0][0].elapsed_time(ev[-1][4])
     if world == 1:
-        phase_ms = [float(np.mean([ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)])) for i in range(4)]
+        # per-phase times: the same iteration through the phase-level entry points, outside the timed region
+        pev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(min(args.steps, 10))]
+        for s in range(len(pev)):
+            pev[s][0].record(stream)
+            eng.phase_phi(it, it > 0); pev[s][1].record(stream)
+            eng.phase_node(); pev[s][2].record(stream)
+            eng.phase_s3(); pev[s][3].record(stream)
+            eng.phase_finish(True); pev[s][4].record(stream)
+            it += 1
+        torch.cuda.synchronize()
+        ev = pev
+    if world == 1:
+        phase_ms = [float(np.mean([ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(len(ev))])) for i in range(4)]
     elif peer:
         mg_ms, _ = eng.mg_timing(False, read=True)
         phase_ms = [mg_ms["wait_b_rows"] + mg_ms["phi+node"], mg_ms["allreduce_sum_s1_s2"] + mg_ms["refresh"] + mg_ms["wait_mphi_rows"],
@@ -360,6 +368,43 @@ def run_ours(args):
         e2e = runner.e2e(step_fn=lambda i: runner.step(i, True, True), it0=it, steps=e2e_steps, nlinks=nlinks, unit=UNIT,
                          heldout=heldout_pairs(n, links, max(2, min(nlinks // 100, 2_000_000))))
         it += e2e_steps + 1
+
+    # ---- second regime: a fraction of the nodes already converged (where real runs live: the recorded reference run
+    # handles 35 % of its links on the one-hot shortcut).  Roofline on the bytes of the rows
+    # actually fetched.
+    late = None
+    if world == 1 and args.converged_frac > 0:
+        rng = np.random.default_rng(0)
+        conv = np.zeros(n, dtype=np.uint32)
+        who = rng.random(n) < args.converged_frac
+        conv[who] = rng.integers(1, k + 1, int(who.sum()))
+        eng.set_state(gamma0, lam0)
+        eng.set_converged(conv)
+        for i in range(3):
+            eng.step(i, True, True)
+        lsteps = max(1, min(args.steps, 10))
+        lev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(lsteps)]
+        for s_ in range(lsteps):
+            lev[s_][0].record(stream)
+            eng.phase_phi(3 + s_, True); lev[s_][1].record(stream)
+            eng.phase_node(); lev[s_][2].record(stream)
+            eng.phase_s3(); lev[s_][3].record(stream)
+            eng.phase_finish(True); lev[s_][4].record(stream)
+        torch.cuda.synchronize()
+        lms = [float(np.mean([lev[s_][i].elapsed_time(lev[s_][i + 1]) for s_ in range(lsteps)])) for i in range(4)]
+        ltot = lev[0][0].elapsed_time(lev[-1][4]) / lsteps
+        cv = eng.get_converged()[0] != 0                 # flags after the timed sweeps (more nodes may have converged)
+        full_links = int((cv[links[:, 0]] == cv[links[:, 1]]).sum())
+        ld_ = info["ld"]
+        lbytes = 2 * full_links * (ld_ * 8 + 4) + 2 * (nlinks - full_links) * 4 + info["segments_phi"] * (2 * ld_ * 8 + 16)
+        lgbs = lbytes / (lms[0] * 1e-3) / 1e9
+        late = {"converged_frac_set": args.converged_frac, "converged_frac_end": float(cv.mean()),
+                "full_phi_link_frac": full_links / nlinks, "ms_per_step": ltot, "value": nlinks / (ltot * 1e-3), "unit": UNIT,
+                "phase_ms": {"phi": lms[0], "node": lms[1], "s3": lms[2], "finish": lms[3]},
+                "roofline": {"bound": "hbm", "achieved": lgbs, "peak": measured_peak_hbm()[0], "unit": "GB/s",
+                             "frac": lgbs / measured_peak_hbm()[0], "algorithmic_bytes_per_launch": int(lbytes),
+                             "note": "phi sweep; bytes of the rows actually fetched (shortcut links fetch no row)"}}
+        it = 0
 
     verify = None
     if not args.no_verify and (world == 1 or peer):
@@ -431,17 +476,20 @@ def run_ours(args):
                      "note": "pull-form bytes of this kernel (DESIGN.md section 4)",
                      "step_gbs_survey_8d_formula": survey_gbs,
                      "step_frac_survey_8d_formula": survey_gbs / peak},
-        "verify": verify, "checksum": checksum,
+        "verify": verify, "checksum": checksum, "late_run": late,
         "exchange": (runner.exchange if world > 1 else None), "mg_phase_ms": (mg_ms if world > 1 else None),
         "setup_s": {"generate": t_gen, "create+upload": t_create},
         "wall_s_timed_region": t_wall,
     }
+    # DRAM traffic of the phi sweep: from the committed `ncu --set full` capture of the same command (it cannot be
+    # measured inside an un-profiled run); the file names its source
     traffic_file = os.path.join(REPO, "profiles", "k_phi_traffic.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and world == 1:
         try:
             tf = json.load(open(traffic_file))
             if tf.get("workload") == args.workload:
                 out["roofline"]["traffic"] = tf.get("dram_bytes_per_launch")
+                out["roofline"]["traffic_source"] = tf.get("source")
         except Exception:
             pass
     if world == 1 and not args.no_cpu_baseline:
@@ -462,33 +510,53 @@ def sample_graph(k, nlinks_sample, avg_deg=200):
 
 
 def cpu_baseline_port(k, budget_s=20.0):
-    """Oracle (C restatement, 1 thread) on a bounded sample; `value` in the bench's unit."""
+    """The oracle (C restatement) on a bounded sample of the workload, on this box's host cores: the serial sweep
+    (oracle/oracle_ls.c -- the reference path itself is serial) and the all-cores sweep (oracle/oracle_ls_omp.c,
+    OpenMP).  `value` (in the bench's unit) is the all-cores figure, `cores` the threads it used; the one-thread figure
+    is reported beside it."""
     sys.path.insert(0, os.path.join(REPO, "tests"))
     import oracle_py as orc
     per_edge_k = 6e-8                                   # ~54-60 ns per (edge,k) on the survey's Xeon
     sweeps = 2
-    ns = int(max(2000, min(2_000_000, budget_s / (sweeps * per_edge_k * k))))
-    n_s, links = sample_graph(k, ns)
-    gamma, lam = fast_state(n_s, k, links)
-    st = orc.State.alloc(n_s, k, links.shape[0])
-    c = st.c
-    c.alpha, c.eta0, c.eta1, c.ones = 1.0 / k, 1.0, 1.0, links.shape[0]
-    st.arr("links")[:] = links
-    tl = np.zeros(n_s); np.add.at(tl, links.ravel().astype(np.int64), 2.0)
-    st.arr("tl")[:] = tl
-    st.arr("gamma")[:] = gamma; st.arr("gammanext")[:] = c.alpha
-    st.arr("lambda_")[:] = lam; st.arr("lambdanext")[:] = lam
-    st.refresh_expectations()
-    st.step(0, 1, 0)                                   # warm
-    t0 = time.perf_counter()
-    for i in range(sweeps):
-        st.step(1 + i, 1, 1)
-    dt = time.perf_counter() - t0
-    st.free()
-    return {"value": links.shape[0] * sweeps / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "oracle/oracle_ls.c, %d sweeps over a synthetic MMSB sample n=%d k=%d links=%d "
-                      "(same generator and average degree as the workload)" % (sweeps, n_s, k, links.shape[0]),
-            "host_cpus": os.cpu_count()}
+    threads = max(1, min(orc.lib().orc_omp_max_threads(), os.cpu_count() or 1))
+    # half of the budget for the serial sweeps, half for the parallel ones (the same number of sweeps, more links)
+    ns1 = int(max(2000, min(2_000_000, 0.5 * budget_s / (sweeps * per_edge_k * k))))
+    nsp = int(max(2000, min(8_000_000, ns1 * max(1, threads // 2))))
+
+    def run(nlinks_sample, nthreads):
+        n_s, links = sample_graph(k, nlinks_sample)
+        gamma, lam = fast_state(n_s, k, links)
+        st = orc.State.alloc(n_s, k, links.shape[0])
+        c = st.c
+        c.alpha, c.eta0, c.eta1, c.ones = 1.0 / k, 1.0, 1.0, links.shape[0]
+        st.arr("links")[:] = links
+        tl = np.zeros(n_s); np.add.at(tl, links.ravel().astype(np.int64), 2.0)
+        st.arr("tl")[:] = tl
+        st.arr("gamma")[:] = gamma; st.arr("gammanext")[:] = c.alpha
+        st.arr("lambda_")[:] = lam; st.arr("lambdanext")[:] = lam
+        st.refresh_expectations()
+        step = (lambda i, wc: st.step(i, 1, wc)) if nthreads == 1 else (lambda i, wc: st.step_omp(1, wc, nthreads))
+        step(0, 0)                                     # warm
+        t0 = time.perf_counter()
+        for i in range(sweeps):
+            step(1 + i, 1)
+        dt = time.perf_counter() - t0
+        st.free()
+        return links.shape[0] * sweeps / dt, n_s, links.shape[0]
+
+    v1, n1, l1 = run(ns1, 1)
+    out = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": "oracle/oracle_ls.c, %d sweeps over a synthetic MMSB sample n=%d k=%d links=%d "
+                     "(same generator and average degree as the workload)" % (sweeps, n1, k, l1),
+           "host_cpus": os.cpu_count()}
+    if threads > 1:
+        vp, np_, lp = run(nsp, threads)
+        out = {"value": vp, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "oracle/oracle_ls_omp.c (OpenMP, %d threads), %d sweeps over a synthetic MMSB sample n=%d k=%d "
+                         "links=%d (same generator and average degree as the workload)" % (threads, sweeps, np_, k, lp),
+               "single_thread": {"value": v1, "cores": 1, "sample": out["sample"]},
+               "host_cpus": os.cpu_count()}
+    return out
 
 
 def cpu_baseline_fa2_port(k, budget_s=15.0):
@@ -591,6 +659,8 @@ def main():
                     help="N > 1: peer = svi_ls_mg_step (rows pushed over peer memory inside the library); "
                          "nccl = torch.distributed collectives between the phases (the library baseline)")
     ap.add_argument("--chunks", type=int, default=0, help="N > 1, peer exchange: pipeline chunks of a shard (0 = default)")
+    ap.add_argument("--converged-frac", type=float, default=0.35,
+                    help="1 GPU: also time the iteration with this fraction of the nodes converged (0 = skip)")
     ap.add_argument("--checksum", type=int, default=0, metavar="S",
                     help="also run S iterations from the start state and print sums of the resulting state")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")

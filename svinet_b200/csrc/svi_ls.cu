@@ -369,15 +369,22 @@ struct svi_ls {
   cudaStream_t side = nullptr, own_main = nullptr, aux = nullptr, up = nullptr;   // aux: node passes, up: "up" segments
   cudaEvent_t ev_phi = nullptr, ev_node = nullptr, ev_up = nullptr;
   cudaEvent_t ev_chunk = nullptr, ev_refresh = nullptr, ev_side = nullptr;
-  // how rows travel to the peers: 0 = one copy-engine transfer per peer on the side stream, 1 = the same transfers
-  // fanned out over one stream per peer, 2 = a small SM kernel (reads a row once, stores it to every peer)
-  int push_mode = 1;
+  // how rows travel to the peers: 0 = one copy-engine transfer per peer on the side stream (default: measured best
+  // at 8 GPUs, 12.2 ms per iteration at config 4), 1 = the same transfers fanned out over one stream per peer (12.7-13.3),
+  // 2 = a small SM kernel that reads a row once and stores it to every peer (12.9; fast pushes, but its blocks displace
+  // the persistent s3 sweep's)
+  int push_mode = 0;
   uint32_t push_blocks = 32;
   cudaStream_t fan[svi::kMaxWorld] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[svi::kMaxWorld] = {};
   uint32_t epoch = 0, gamma_epoch = 0;
   bool gamma_wait = false;       // svi_ls_mg_publish_gamma ran: the next svi_ls_get_state awaits the peers' rows
   uint32_t *d_mg_err = nullptr;
+  // svi_ls_step as a CUDA graph, one per (active-set branch, tally, annealing, converged-buffer parity): the
+  // iteration is ~10 dependent launches, which at small sizes (config 2: 17 903 nodes, K = 20) cost more than the kernels
+  cudaGraphExec_t graphs[16] = {};
+  cudaStream_t cap = nullptr;
+  bool use_graph = true;
   // optional per-phase timing of svi_ls_mg_step (svi_ls_mg_timing): events on the main stream, ring of steps
   static constexpr int kTimedSteps = 32, kMarks = 9, kSideMarks = 4;
   bool timing = false;
@@ -417,6 +424,9 @@ void free_all(svi_ls *h) {
   for (auto &row : h->sev)
     for (cudaEvent_t ev : row)
       if (ev) cudaEventDestroy(ev);
+  for (cudaGraphExec_t g : h->graphs)
+    if (g) cudaGraphExecDestroy(g);
+  if (h->cap) cudaStreamDestroy(h->cap);
   for (cudaStream_t st : h->fan)
     if (st) cudaStreamDestroy(st);
   for (cudaEvent_t ev : h->ev_join)
@@ -715,6 +725,7 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   P.conv = h->d_conv2[0]; P.conv_next = h->d_conv2[1]; P.active = h->d_active; P.abits = h->d_abits; P.mbits = h->d_mbits;
   h->nlo = std::move(nlo);
   h->nup = std::move(nup);
+  if (const char *ng = getenv("SVI_LS_NO_GRAPH")) h->use_graph = !(ng[0] == '1');
   h->he_prefix.assign(nlocal + 1, 0);
   for (uint32_t v = 0; v < nlocal; ++v) h->he_prefix[v + 1] = h->he_prefix[v] + deg_lo[v] + deg_up[v];
   *out = h;
@@ -957,12 +968,50 @@ int svi_ls_phase_lambda(svi_ls *h, int annealing) {
   return SVI_OK;
 }
 
+// the whole iteration on stream `st` (== phase_phi; phase_node; phase_s3; phase_finish without the host-side flip)
+static int enqueue_step(svi_ls *h, cudaStream_t st, uint32_t iter, int annealing, int write_comm) {
+  const Params &P = h->P;
+  int rc = begin_iteration(h, st, write_comm);
+  if (rc) return rc;
+  launch_phi(h, st, st, iter, write_comm, 0, P.nseg_lo, P.nseg_lo, P.nseg);
+  launch_node(h, st, P.node_begin, P.node_end, 0);
+  svi::k_reduce_kpart<<<4, 256, 0, st>>>(h->d_kpart, h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec, h->d_kvec, P.ld);
+  launch_s3(h, st);
+  h->ops.lambda(P, st, annealing, 1);
+  h->ops.refresh(P, st, true);
+  CK(cudaGetLastError());
+  return SVI_OK;
+}
+
 int svi_ls_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
+  if (!h) return fail(SVI_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  const bool sparse = iter > 1000 && h->P.k_div10 > 0;
   int rc;
-  if ((rc = svi_ls_phase_phi(h, iter, write_comm))) return rc;
-  if ((rc = svi_ls_phase_node(h))) return rc;
-  if ((rc = svi_ls_phase_s3(h))) return rc;
-  return svi_ls_phase_finish(h, annealing);
+  if (!h->use_graph || h->force_partition || h->partition_every_sweep || h->conv_pending || h->mg) {
+    if ((rc = enqueue_step(h, h->stream, iter, annealing, write_comm))) return rc;
+    flip_converged(h);
+    return SVI_OK;
+  }
+  const int key = (sparse ? 1 : 0) | (write_comm ? 2 : 0) | (annealing ? 4 : 0) | (h->cur ? 8 : 0);
+  if (!h->graphs[key]) {
+    if (!h->cap) CK(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_step(h, h->cap, sparse ? 1001u : 0u, annealing, write_comm);
+    const cudaError_t e = cudaStreamEndCapture(h->cap, &g);
+    if (rc) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(SVI_ERR_CUDA, "svi_ls_step: graph capture failed: %s", cudaGetErrorString(e));
+    const cudaError_t ei = cudaGraphInstantiate(&h->graphs[key], g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) return fail(SVI_ERR_CUDA, "svi_ls_step: cudaGraphInstantiate: %s", cudaGetErrorString(ei));
+  }
+  CK(cudaGraphLaunch(h->graphs[key], h->stream));
+  flip_converged(h);
+  return SVI_OK;
 }
 
 // ---- multi-GPU over peer memory (svi_ls_mg.cuh) ------------------------------------------------------------------
