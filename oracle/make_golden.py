@@ -44,9 +44,15 @@ CASES = {
     "c2_m25": ("ca-AstroPh.csv", 17903, 20, ["-max-iterations", "25", "-no-stop"], "n17903-k20-mmsb-linksampling"),
     "c1_etasparse_m10": ("assort-75-4.txt", 75, 4, ["-max-iterations", "10", "-no-stop", "-eta-type", "sparse"],
                          "n75-k4-mmsb-linksampling"),
+    # -init-communities (init_gamma_external, linksampling.cc:404-452): gamma starts from given communities, no RNG
+    "c1_initcomm_m10": ("assort-75-4.txt", 75, 4, ["-max-iterations", "10", "-no-stop", "-init-communities",
+                                                   "assort-75-4-init-communities.txt"], "n75-k4-mmsb-linksampling"),
     # the natural run: the validation stop ends it (iteration 30 here); small files only
     "c2_natural": ("ca-AstroPh.csv", 17903, 20, [], "n17903-k20-mmsb-linksampling"),
 }
+# extra input files a case needs in its cwd (committed under tests/golden/inputs/)
+EXTRA_INPUTS = {"c1_initcomm_m10": ["assort-75-4-init-communities.txt"]}
+KEEP_EXTRA = {"c1_initcomm_m10": ["init_memberships.txt"]}
 KEEP_ONLY = {"c2_natural": ["lambda.txt", "communities.txt", "validation.txt", "max.txt", "validation-edges.txt", "param.txt"]}
 
 # `-rnode -stratified` (class FastAMM2): name -> (input, n, k, flags, outdir)
@@ -92,6 +98,8 @@ def main():
             continue
         scratch = tempfile.mkdtemp(prefix="golden_")
         shutil.copy(os.path.join(DATA, fname), os.path.join(scratch, fname))
+        for extra in EXTRA_INPUTS.get(name, []):
+            shutil.copy(os.path.join(GOLD, "inputs", extra), os.path.join(scratch, extra))
         cmd = [REF_BIN, "-file", fname, "-n", str(n), "-k", str(k)] + mode.split() + flags
         with open(os.path.join(scratch, "stdout.log"), "w") as log:
             rc = subprocess.call(cmd, cwd=scratch, stdout=log, stderr=subprocess.STDOUT)
@@ -102,7 +110,9 @@ def main():
         shutil.rmtree(dst, ignore_errors=True)
         os.makedirs(dst)
         entry = {"input": fname, "n": n, "k": k, "flags": flags, "outdir": outdir, "md5": {}, "mode": mode}
-        for f in KEEP_ONLY.get(name, keep):
+        if name in EXTRA_INPUTS:
+            entry["extra_inputs"] = EXTRA_INPUTS[name]
+        for f in KEEP_ONLY.get(name, keep) + KEEP_EXTRA.get(name, []):
             p = os.path.join(src, f)
             if not os.path.exists(p):
                 continue

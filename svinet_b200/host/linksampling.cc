@@ -4,6 +4,7 @@
 #include "fixed_fmt.hh"
 #include "textio.hh"
 #include "pool.hh"
+#include "nmi.hh"
 
 #include <algorithm>
 #include <cassert>
@@ -13,6 +14,7 @@
 #include <cstring>
 #include <chrono>
 #include <condition_variable>
+#include <map>
 #include <mutex>
 #include <sstream>
 #include <thread>
@@ -119,13 +121,18 @@ LinkSampling::LinkSampling(Env &env, Network &network)
   if (env_.load_test) fprintf(stderr, "svinet: -load-test is accepted but the test set is not used in this build\n");
   lap("held-out draw");
 
+  if (env_.nmi) load_ground_truth();                             // network.cc:120-123
+
   gamma_.assign((size_t)n_ * k_, 0.0);
   lambda_.assign((size_t)k_ * 2, 0.0);
   if (env_.model_load) {
     if (load_model() < 0) exit(-1);
   } else if (env_.use_init_communities) {
-    fprintf(stderr, "svinet: -init-communities is not part of this build\n");
-    exit(-1);
+    init_gamma_external();
+    for (uint32_t c = 0; c < k_; ++c) {                          // init_lambda, :364-372 (:115-116)
+      lambda_[2 * c] = env_.eta0;
+      lambda_[2 * c + 1] = env_.eta1;
+    }
   } else {
     init_gamma2();
     for (uint32_t c = 0; c < k_; ++c) {                          // init_lambda, :364-372
@@ -309,6 +316,89 @@ void LinkSampling::load_validation() {
   validation_sorted_.erase(std::unique(validation_sorted_.begin(), validation_sorted_.end()), validation_sorted_.end());
   for (const Edge &e : validation_sorted_) held_keys_.insert(((uint64_t)e.first << 32) | e.second);
   env_.plog("link sampling: loaded validation heldout pairs:", cnt);
+}
+
+// -init-communities <file>: one community per line (external node ids), Network::load_init_communities
+// (src/network.cc:374-437; it also writes init_memberships.txt), then init_gamma_external (:404-452): every node p
+// adds, ONCE PER ADJACENCY ENTRY, the normalised vector phi_p[k] = alpha + [k in communities(p)] * n / |communities(p)|
+// to its row (the reference's loop body does not depend on the neighbour; the repeated addition is kept, it is what
+// defines the rounding).  No RNG use.
+void LinkSampling::init_gamma_external() {
+  FILE *f = fopen(env_.init_communities_fname.c_str(), "r");
+  if (!f) {
+    printf("cannot open init communities file:%s\n", strerror(errno));
+    exit(-1);
+  }
+  printf("+ Loading init communities from %s\n", env_.init_communities_fname.c_str());
+  std::vector<std::vector<uint32_t>> member(n_);        // _init_communities_seq: communities of every node, file order
+  uint32_t cid = 0;
+  {
+    char *line = nullptr;
+    size_t cap = 0;
+    ssize_t len;
+    while ((len = getline(&line, &cap, f)) > 0) {
+      // (the reference scans "%[^\n]" first: an empty line keeps the PREVIOUS line's text in its buffer and repeats
+      // that community under a new id; such files are refused here instead of reproducing the accident)
+      char *p = line, *e = nullptr;
+      bool any = false;
+      for (;; p = e) {
+        const long u = strtol(p, &e, 10);
+        if (p == e) break;
+        uint32_t seq;
+        if (u < 0 || !net_.id2seq((uint32_t)u, &seq)) {
+          fprintf(stderr, "error: init-communities id %ld not found in original network\n", u);
+          exit(-1);
+        }
+        if (seq < n_) member[seq].push_back(cid);
+        any = true;
+      }
+      if (!any) {
+        int c = fgetc(f);
+        if (c == EOF) break;                       // trailing blank line
+        fprintf(stderr, "error: line %u of %s lists no node\n", cid + 1, env_.init_communities_fname.c_str());
+        exit(-1);
+      }
+      cid++;
+    }
+    free(line);
+  }
+  fclose(f);
+  printf("+ Loaded %d init communities\n", cid);
+  if (FILE *g = fopen(env_.file("/init_memberships.txt").c_str(), "w")) {
+    for (uint32_t i = 0; i < n_; ++i) {
+      fprintf(g, "%d\t", net_.seq2id(i));
+      for (uint32_t c : member[i]) fprintf(g, "%d\t", c);
+      fprintf(g, "\n");
+    }
+    fclose(g);
+  }
+  for (uint32_t i = 0; i < n_; ++i)
+    for (uint32_t c : member[i])
+      if (c >= k_) {   // the reference only logs this and then writes past the end of phi (:437-439)
+        fprintf(stderr, "error: init community %u of node %d, but -k is %u\n", c, net_.seq2id(i), k_);
+        exit(-1);
+      }
+  const uint32_t k = k_;
+  const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t)
+    th.emplace_back([&, t] {
+      std::vector<double> phi(k);
+      const uint32_t v0 = (uint32_t)((uint64_t)n_ * t / nt), v1 = (uint32_t)((uint64_t)n_ * (t + 1) / nt);
+      for (uint32_t p = v0; p < v1; ++p) {
+        double *g = &gamma_[(size_t)p * k];
+        for (uint32_t c = 0; c < k; ++c) g[c] = env_.alpha;                 // _gamma.set_elements(alpha)
+        for (uint32_t c = 0; c < k; ++c) phi[c] = env_.alpha;
+        for (uint32_t c : member[p]) phi[c] += (double)n_ / member[p].size();
+        double s = .0;                                                       // D1Array::normalize, matrix.hh:341-346
+        for (uint32_t c = 0; c < k; ++c) s += phi[c];
+        for (uint32_t c = 0; c < k; ++c) phi[c] = phi[c] / s;
+        const size_t deg = net_.get_edges(p).size();
+        for (size_t r = 0; r < deg; ++r)                                     // _gamma.add_slice(p, phi), once per entry
+          for (uint32_t c = 0; c < k; ++c) g[c] += phi[c];
+      }
+    });
+  for (auto &x : th) x.join();
 }
 
 void LinkSampling::init_gamma2() {
@@ -581,9 +671,65 @@ void LinkSampling::write_communities(const std::string &name) {
   fclose(f);
 }
 
+// -nmi <file>: "<node id>\t<community> <community> ..." per line (Network::load_ground_truth, network.cc:254-307);
+// ground_truth.txt / ground_truth_community_sizes.txt as write_gt_communities (:508-536) writes them: communities in
+// ascending id order, members in file order.
+void LinkSampling::load_ground_truth() {
+  FILE *f = fopen(env_.ground_truth_fname.c_str(), "r");
+  if (!f) {
+    fprintf(stderr, "error: cannot read ground truth file %s; check path; skipping file\n", env_.ground_truth_fname.c_str());
+    return;
+  }
+  std::map<uint32_t, std::vector<uint32_t>> by_id, by_seq;
+  char *line = nullptr;
+  size_t cap = 0;
+  while (getline(&line, &cap, f) > 0) {
+    char *e = nullptr;
+    const long nid = strtol(line, &e, 10);
+    if (e == line) continue;
+    uint32_t seq;
+    if (nid < 0 || !net_.id2seq((uint32_t)nid, &seq)) {
+      fprintf(stderr, "error: ground truth node %ld is not in the network\n", nid);
+      exit(-1);
+    }
+    for (char *p = e;; p = e) {
+      const long u = strtol(p, &e, 10);
+      if (p == e) break;
+      by_id[(uint32_t)u].push_back((uint32_t)nid);
+      by_seq[(uint32_t)u].push_back(seq);
+    }
+  }
+  free(line);
+  fclose(f);
+  printf("+ Done loading ground truth\n");
+  FILE *g = open_or_die(env_.file("/ground_truth.txt"), "w", "ground truth");
+  FILE *sz = open_or_die(env_.file("/ground_truth_community_sizes.txt"), "w", "ground truth sizes");
+  uint32_t c = 0;
+  for (const auto &kv : by_id) {
+    fprintf(sz, "%d\t%ld\n", c++, (long)kv.second.size());
+    for (uint32_t v : kv.second) fprintf(g, "%d ", v);
+    fprintf(g, "\n");
+  }
+  fclose(g);
+  fclose(sz);
+  for (auto &kv : by_seq) gt_communities_.push_back(std::move(kv.second));
+}
+
 void LinkSampling::log_communities() {
   write_communities("/communities.txt");
-  if (env_.nmi) fprintf(stderr, "svinet: -nmi needs the external `mutual` binary and is skipped in this build\n");
+  if (env_.nmi && !gt_communities_.empty()) {
+    // the reference appends the output of the external `mutual` binary here (:843-851); nmi.hh is that measure
+    const uint32_t words = (k_ + 31) / 32;
+    std::vector<std::vector<uint32_t>> found(k_);
+    if (member_bits_.size() == (size_t)n_ * words)
+      for (uint32_t p = 0; p < n_; ++p)
+        for (uint32_t c = 0; c < k_; ++c)
+          if (member_bits_[(size_t)p * words + c / 32] >> (c % 32) & 1u) found[c].push_back(p);
+    if (FILE *f = fopen(env_.file("/mutual.txt").c_str(), "a")) {
+      fprintf(f, "mutual3:\t%g\n", nmi::lfk(n_, gt_communities_, found));
+      fclose(f);
+    }
+  }
 }
 
 void LinkSampling::do_on_stop() {

@@ -40,12 +40,15 @@ class LinkSampling {
   void get_random_edge(bool link, Edge &e);   // src/linksampling.hh:328-349
   bool edge_ok(const Edge &e) const;      // src/linksampling.hh:296-326
   void init_gamma2();                     // :374-401
+  void init_gamma_external();             // :404-452 (-init-communities) + Network::load_init_communities, network.cc:374-437
   int load_model();                       // :1266-1352
   void assign_training_links();           // :493-523
   // --- per report ---
   bool validation_likelihood();           // :966-1050, true = the run must end
   void test_likelihood_line();            // :1147-1182 on the (always empty) test set
   void log_communities();                 // :839-852
+  void load_ground_truth();               // Network::load_ground_truth + write_gt_communities, network.cc:254-307,508-536
+  std::vector<std::vector<uint32_t>> gt_communities_;   // -nmi: ground-truth communities as seq ids
   void write_communities(const std::string &name);   // :882-917
   void write_groups();                    // :1452-1476
   void do_on_stop();                      // :792-802

@@ -24,10 +24,10 @@ def cli():
 
 def run_case(cli, case, d, extra=(), env=None):
     ent = MANIFEST[case]
-    inp = input_path(ent["input"], d)
-    local = os.path.join(d, ent["input"])
-    if not os.path.exists(local):
-        os.symlink(inp, local)
+    for name in [ent["input"]] + ent.get("extra_inputs", []):
+        inp, local = input_path(name, d), os.path.join(d, name)
+        if not os.path.exists(local):
+            os.symlink(inp, local)
     cmd = [cli, "-file", ent["input"], "-n", str(ent["n"]), "-k", str(ent["k"]), "-link-sampling"] + ent["flags"] + list(extra)
     p = subprocess.run(cmd, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=600,
                        env=dict(os.environ, **(env or {})))
@@ -36,7 +36,8 @@ def run_case(cli, case, d, extra=(), env=None):
 
 
 @pytest.mark.parametrize("case", ["c1_m30", "c1_natural", "c1_m1", "c1_seed7_m12", "c1_accuracy_m8", "c1_k7_m15",
-                                  "lfr_k28_m20", "c2_m12", "c2_m25", "c2_natural", "c1_etasparse_m10"])  # the -link-sampling fixtures
+                                  "lfr_k28_m20", "c2_m12", "c2_m25", "c2_natural", "c1_etasparse_m10",
+                                  "c1_initcomm_m10"])  # the -link-sampling fixtures
 def test_cli_output_directory_matches_reference(cli, case):
     with Scratch() as d:
         ent, out = run_case(cli, case, d)
@@ -83,6 +84,33 @@ def test_cli_gpus_n_writes_the_reference_directory(cli, case, gpus):
             assert open(os.path.join(out, fname)).read() == golden_text(case, fname), fname
         nf, noff = flips["gamma.txt"]
         assert noff <= max(2, nf // 1000), flips
+
+
+def test_cli_nmi_on_lfr_benchmark(cli):
+    """the LFR example run to its validation stop with -nmi <ground truth>.  The reference's
+    recorded run ends at NMI 0.897 (example/n1000-k28-LFR-linksampling.tgz: mutual.txt, from the external `mutual`
+    binary); the CLI computes the same measure itself (host/nmi.hh), one `mutual3:` line per report."""
+    import nmi_lfk
+    from test_nmi import as_matrix, lfr_ground_truth
+    ent = MANIFEST["lfr_k28_m20"]
+    with Scratch() as d:
+        for name in (ent["input"], "LFR-ground-truth-n1000-k28.txt"):
+            inp, local = input_path(name, d), os.path.join(d, name)
+            if not os.path.exists(local):
+                os.symlink(inp, local)
+        cmd = [cli, "-file", ent["input"], "-n", "1000", "-k", "28", "-link-sampling", "-nmi", "LFR-ground-truth-n1000-k28.txt"]
+        p = subprocess.run(cmd, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=600)
+        assert p.returncode == 0, p.stderr.decode()
+        out = os.path.join(d, ent["outdir"])
+        lines = open(os.path.join(out, "mutual.txt")).read().strip().split("\n")
+        assert all(ln.startswith("mutual3:\t") for ln in lines) and len(lines) > 20
+        final = float(lines[-1].split("\t")[1])
+        assert final >= 0.85, lines[-5:]
+        index, gt = lfr_ground_truth()
+        found = [[index[int(t)] for t in ln.split()] for ln in open(os.path.join(out, "communities.txt")) if ln.strip()]
+        assert abs(nmi_lfk.nmi_lfk(as_matrix(1000, gt), as_matrix(1000, found)) - final) < 2e-6      # printed with %g
+        gt_lines = open(os.path.join(out, "ground_truth.txt")).read().strip().split("\n")
+        assert len(gt_lines) == 28
 
 
 FA2_CASES = [c for c in MANIFEST if MANIFEST[c].get("mode") == "-rnode -stratified"]

@@ -25,10 +25,10 @@ def cli():
 
 def run_dump(cli, case, d, extra=()):
     ent = MANIFEST[case]
-    inp = input_path(ent["input"], d)
-    local = os.path.join(d, ent["input"])
-    if not os.path.exists(local):
-        os.symlink(inp, local)
+    for name in [ent["input"]] + ent.get("extra_inputs", []):
+        inp, local = input_path(name, d), os.path.join(d, name)
+        if not os.path.exists(local):
+            os.symlink(inp, local)
     dump = os.path.join(d, "dump")
     os.makedirs(dump, exist_ok=True)
     cmd = [cli, "-file", ent["input"], "-n", str(ent["n"]), "-k", str(ent["k"]), "-link-sampling"] + ent["flags"] + \
@@ -112,6 +112,36 @@ def test_ragged_input_selfloops_duplicates_and_single_nodes(cli):
         # node 99 only has a self-loop: it exists, has no links and an all-zero initial gamma row
         assert np.all(gamma[4] == 0)                                    # ids in first-appearance order: 99 -> seq 4
         m.close(); g.close()
+
+
+def test_init_communities_startup_state(cli):
+    """-init-communities <file> (init_gamma_external, linksampling.cc:404-452; Network::load_init_communities,
+    network.cc:374-437): gamma[p] = alpha + one normalised vector added once per adjacency entry; no RNG.
+    init_memberships.txt must equal the reference's byte for byte, the start-up gamma a literal restatement."""
+    with Scratch() as d:
+        ent, got = run_dump(cli, "c1_initcomm_m10", d)
+        assert open(os.path.join(got["outdir"], "init_memberships.txt")).read() == golden_text("c1_initcomm_m10", "init_memberships.txt")
+        n, k, alpha = 75, 4, 0.25
+        g = orc.Graph.read(input_path(ent["input"], d), n)
+        id2seq = {int(v): i for i, v in enumerate(g.seq2id[:n])}
+        member = [[] for _ in range(n)]
+        for cid, line in enumerate(open(input_path("assort-75-4-init-communities.txt", d))):
+            for tok in line.split():
+                member[id2seq[int(tok)]].append(cid)
+        want = np.full((n, k), alpha)
+        for p_ in range(n):
+            phi = np.full(k, alpha)
+            for c in member[p_]:
+                phi[c] += n / len(member[p_])
+            s_ = 0.0
+            for c in range(k):
+                s_ += phi[c]
+            phi = phi / s_
+            for _ in range(int(g.adj_off[p_ + 1] - g.adj_off[p_])):
+                want[p_] += phi
+        assert np.array_equal(got["gamma"], want)
+        assert np.array_equal(got["lambda"], np.ones((k, 2)))
+        g.close()
 
 
 def test_cli_refuses_other_engines(cli):
