@@ -113,6 +113,70 @@ def test_cli_nmi_on_lfr_benchmark(cli):
         assert len(gt_lines) == 28
 
 
+@pytest.mark.parametrize("case", ["c1_m30", "lfr_k28_m20"])
+def test_reference_gml_consumer_reads_our_output(cli, case):
+    """The consumer of this path's files: `svinet -gml` (MMSBGen::gml, src/mmsbgen.cc:74-149,911) loads gamma.txt /
+    lambda.txt from its cwd.  The UNMODIFIED reference binary (oracle/_ref/svinet_ref) is run once on the reference's
+    own files (the fixture) and once on the files the B200 CLI wrote: the GML and the statistics it derives must agree
+    (same link-community group of every node, same integer counts; decimals within the last printed digits)."""
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "svinet_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/svinet_ref not built (needs /root/reference at build time)")
+    with Scratch() as d:
+        ent, out = run_case(cli, case, d)
+        results = {}
+        for tag in ("reference", "ours"):
+            w = os.path.join(d, "gml_" + tag)
+            os.makedirs(w)
+            os.symlink(input_path(ent["input"], d), os.path.join(w, ent["input"]))
+            for f in ("gamma.txt", "lambda.txt"):
+                text = golden_text(case, f) if tag == "reference" else open(os.path.join(out, f)).read()
+                open(os.path.join(w, f), "w").write(text)
+            p = subprocess.run([ref, "-file", ent["input"], "-n", str(ent["n"]), "-k", str(ent["k"]), "-gml"], cwd=w,
+                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+            assert p.returncode == 0 and b"Done writing GML file" in p.stdout, p.stdout.decode()[-400:]
+            results[tag] = {f: open(os.path.join(w, "gml", f)).read() for f in
+                            ("network.gml", "community_stats.txt", "node_bridgeness.txt", "node_influence.txt",
+                             "number_of_memberships.txt")}
+        for f in results["ours"]:
+            a, b = results["ours"][f].split("\n"), results["reference"][f].split("\n")
+            assert len(a) == len(b), f
+            for la, lb in zip(a, b):
+                ta, tb = la.split(), lb.split()
+                assert len(ta) == len(tb), (f, la, lb)
+                for x, y in zip(ta, tb):
+                    if x == y:
+                        continue
+                    assert "." in y and abs(float(x) - float(y)) <= 2e-4 * max(1.0, abs(float(y))), (f, la, lb)
+
+
+@pytest.mark.parametrize("case", ["c1_m30", "c1_natural", "lfr_k28_m20"])
+def test_reference_host_code_over_the_library(cli, case):
+    """INTEGRATION.md option B, executed (oracle/ref_b200.py, `make -C oracle ref_b200`): the reference's OWN
+    LinkSampling -- its constructor, RNG, held-out draw, stop machine, writers -- with the loop body replaced by
+    svi_ls_step and the three consumers fed from the device.  Its output directory must equal the stock reference's
+    (the committed fixture)."""
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "svinet_ref_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/svinet_ref_b200 not built (needs /root/reference at build time)")
+    ent = MANIFEST[case]
+    with Scratch() as d:
+        inp, local = input_path(ent["input"], d), os.path.join(d, ent["input"])
+        if not os.path.exists(local):
+            os.symlink(inp, local)
+        cmd = [exe, "-file", ent["input"], "-n", str(ent["n"]), "-k", str(ent["k"]), "-link-sampling"] + ent["flags"]
+        p = subprocess.run(cmd, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=900)
+        assert p.returncode == 0, p.stderr.decode()[-500:]
+        out = os.path.join(d, ent["outdir"])
+        for fname in ("gamma.txt", "lambda.txt", "groups.txt", "validation.txt", "max.txt"):
+            got = open(os.path.join(out, fname)).read()
+            nf, noff = compare_numeric_text(got, golden_text(case, fname),
+                                            skip_cols=(1,) if fname in ("validation.txt", "max.txt") else ())
+            assert noff <= max(2, nf // 1000), (fname, nf, noff)
+        for fname in ("communities.txt", "validation-edges.txt"):
+            assert open(os.path.join(out, fname)).read() == golden_text(case, fname), fname
+
+
 FA2_CASES = [c for c in MANIFEST if MANIFEST[c].get("mode") == "-rnode -stratified"]
 
 
