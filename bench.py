@@ -494,6 +494,20 @@ def run_ours(args):
             pass
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_port(k, budget_s=args.cpu_budget)
+    if world == 1 and not args.no_fa2:
+        # the declared secondary path (-rnode -stratified, class FastAMM2): its own
+        # measurement (bench_fa2.py) at config 3, embedded so that the driver's run carries it
+        try:
+            eng.close()
+            del eng
+            torch.cuda.empty_cache()
+            import bench_fa2
+            fa = bench_fa2.run(argparse.Namespace(workload="c3", steps=200, warmup=10, report=100, no_cpu_baseline=True,
+                                                  cpu_budget=0.0))
+            out["secondary_path_fa2"] = {key: fa[key] for key in ("metric", "value", "unit", "ms_per_step", "iterations_per_s",
+                                                                  "config", "e2e", "roofline", "gpu_launches")}
+        except Exception as exc:          # never lose the main line over the secondary measurement
+            out["secondary_path_fa2"] = {"error": repr(exc)}
     print(json.dumps(out))
     sys.stdout.flush()
     if world > 1:
@@ -655,6 +669,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true", help="(default on at 1 GPU) recompute sampled gamma rows on the host")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-fa2", action="store_true", help="skip the embedded bench_fa2 record (secondary path)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer = svi_ls_mg_step (rows pushed over peer memory inside the library); "
                          "nccl = torch.distributed collectives between the phases (the library baseline)")

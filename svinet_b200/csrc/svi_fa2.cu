@@ -118,6 +118,13 @@ struct svi_fa2 {
   Fa2Ctrl *h_ctrl = nullptr;   // pinned staging for step()
   uint32_t *h_pairs = nullptr; // pinned staging for the pair list
   size_t h_pairs_cap = 0;
+  // step(): TWO sets of pinned staging (pair list + control block) used alternately, each guarded by an event
+  // recorded after its upload, so the host stages minibatch i+1 while the device still runs minibatch i
+  Fa2Ctrl *st_ctrl[2] = {nullptr, nullptr};
+  uint32_t *st_pairs[2] = {nullptr, nullptr};
+  size_t st_cap[2] = {0, 0};
+  cudaEvent_t st_done[2] = {nullptr, nullptr};
+  int st_slot = 0;
 };
 
 namespace {
@@ -169,7 +176,7 @@ void launch_iteration(svi_fa2 *h, uint64_t nodec) {
   h->ops.prep(h->P, h->stream);
   h->ops.pairs(h->P, h->stream);
   if (!h->P.lazy) h->ops.blend(h->P, h->stream);
-  svi::k_fa2_lambda<<<1, 256, 0, h->stream>>>(h->P, (uint32_t)h->ops.cap);
+  svi::k_fa2_lambda<<<1, 256, 0, h->stream>>>(h->P, (uint32_t)h->ops.cap, 128u / (uint32_t)h->ops.lanes);
   if (h->P.lazy) {
     // c shrinks by (1 - rho) per iteration: exp(-2 sqrt(T)) in the long run.  Re-base the stored rows long
     // before c*u leaves the FP64 range (every ~2e4 iterations at the default step sizes).
@@ -270,6 +277,11 @@ void svi_fa2_destroy(svi_fa2 *h) {
     if (p) cudaFree(p);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
   if (h->h_pairs) cudaFreeHost(h->h_pairs);
+  for (int i = 0; i < 2; ++i) {
+    if (h->st_ctrl[i]) cudaFreeHost(h->st_ctrl[i]);
+    if (h->st_pairs[i]) cudaFreeHost(h->st_pairs[i]);
+    if (h->st_done[i]) cudaEventDestroy(h->st_done[i]);
+  }
   delete h;
 }
 
@@ -341,22 +353,29 @@ int svi_fa2_step(svi_fa2 *h, uint32_t iter, uint32_t type, uint32_t start, uint6
   DevGuard guard(h->device);
   int rc = ensure_pairs(h, npairs);
   if (rc) return rc;
-  // the previous step may still be reading the pinned staging buffers
-  SVI_CK(cudaStreamSynchronize(h->stream));
-  if (npairs > h->h_pairs_cap) {
-    if (h->h_pairs) cudaFreeHost(h->h_pairs);
-    h->h_pairs = nullptr;
-    h->h_pairs_cap = 0;
-    SVI_CK(cudaMallocHost((void **)&h->h_pairs, std::max<uint64_t>(npairs, 1024) * 2 * sizeof(uint32_t)));
-    h->h_pairs_cap = std::max<uint64_t>(npairs, 1024);
+  // staging slot: wait only for the upload that used this slot two steps ago (not for the device to go idle)
+  const int slot = h->st_slot ^= 1;
+  if (!h->st_done[slot]) {
+    SVI_CK(cudaEventCreateWithFlags(&h->st_done[slot], cudaEventDisableTiming));
+    SVI_CK(cudaMallocHost((void **)&h->st_ctrl[slot], sizeof(Fa2Ctrl)));
+  } else {
+    SVI_CK(cudaEventSynchronize(h->st_done[slot]));
+  }
+  if (npairs > h->st_cap[slot]) {
+    if (h->st_pairs[slot]) cudaFreeHost(h->st_pairs[slot]);
+    h->st_pairs[slot] = nullptr;
+    h->st_cap[slot] = 0;
+    const size_t cap = std::max<uint64_t>(npairs + npairs / 4, 1024);
+    SVI_CK(cudaMallocHost((void **)&h->st_pairs[slot], cap * 2 * sizeof(uint32_t)));
+    h->st_cap[slot] = cap;
   }
   if (npairs) {
-    memcpy(h->h_pairs, pairs, npairs * 2 * sizeof(uint32_t));
-    SVI_CK(cudaMemcpyAsync(h->d_pairs, h->h_pairs, npairs * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    memcpy(h->st_pairs[slot], pairs, npairs * 2 * sizeof(uint32_t));
+    SVI_CK(cudaMemcpyAsync(h->d_pairs, h->st_pairs[slot], npairs * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   }
   const svi_fa2_config &c = h->cfg;
   // only the per-iteration half of the control block is written: the device keeps the counters
-  Fa2Ctrl *hc = h->h_ctrl;
+  Fa2Ctrl *hc = h->st_ctrl[slot];
   hc->type = type; hc->start = start; hc->npairs = (uint32_t)npairs; hc->iter = iter;
   hc->sampled_inc = npairs;
   hc->rho_node = std::pow(c.nodetau0 + (double)h->nodec, -1 * c.nodekappa);             // src/fastamm2.cc:606
@@ -364,6 +383,7 @@ int svi_fa2_step(svi_fa2 *h, uint32_t iter, uint32_t type, uint32_t start, uint6
   hc->scale = type == 0 ? (double)c.n / (2 * (1 - c.inf_epsilon))                       // :591-592
                         : ((double)c.n * (double)c.m_sets) / (2 * c.inf_epsilon);
   SVI_CK(cudaMemcpyAsync(h->d_ctrl, hc, offsetof(Fa2Ctrl, nodec), cudaMemcpyHostToDevice, h->stream));
+  SVI_CK(cudaEventRecord(h->st_done[slot], h->stream));
   launch_iteration(h, h->nodec);
   h->nodec++;
   SVI_CK(cudaGetLastError());

@@ -351,7 +351,9 @@ __global__ void __launch_bounds__(T) k_fa2_blend(const Fa2Params P) {
         if (col >= P.ld) continue;
         double2 t = make_double2(0.0, 0.0);
         if (is_start) {
-          for (uint32_t b = 0; b < P.pair_blocks; ++b) {
+          // (only the pair-kernel blocks that had pairs: the others' partials are zero)
+          const uint32_t active = min(P.pair_blocks, (c.npairs + (uint32_t)(T / G) - 1u) / (uint32_t)(T / G));
+          for (uint32_t b = 0; b < active; ++b) {
             const double2 v = *reinterpret_cast<const double2 *>(P.partS + (size_t)b * CAP + col);
             t.x += v.x;
             t.y += v.y;
@@ -369,26 +371,35 @@ __global__ void __launch_bounds__(T) k_fa2_blend(const Fa2Params P) {
 }
 
 // ---- lambda blend (src/fastamm2.cc:626-638) + counters ----------------------------------------------
-static __global__ void k_fa2_lambda(const Fa2Params P, uint32_t cap) {
+// One block.  The column sums over the pair kernel's block partials are taken by one WARP per column (lane l adds
+// the blocks l, l+32, ... in order, then a fixed butterfly) over the blocks that had pairs only: the first version
+// walked all 296 partials in one thread per column, 250 us per launch at K = 4.
+static __global__ void __launch_bounds__(256) k_fa2_lambda(const Fa2Params P, uint32_t cap, uint32_t groups_per_block) {
   const Fa2Ctrl c = *P.ctrl;
-  if (P.lazy) {   // the start row: u += rho*scale*(sum of its phis) / c'   (eager mode: k_fa2_blend does it)
-    const double coef = c.rho_node * c.scale / ((1.0 - c.rho_node) * c.cscale);
-    double *urow = P.gamma + (size_t)c.start * P.ld;
-    for (uint32_t z = threadIdx.x; z < P.k; z += blockDim.x) {
-      double s = 0.0;
-      for (uint32_t b = 0; b < P.pair_blocks; ++b) s += P.partS[(size_t)b * cap + z];
-      urow[z] = fma(coef, s, urow[z]);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t active = min(P.pair_blocks, (c.npairs + groups_per_block - 1u) / groups_per_block);
+  const double coef = c.rho_node * c.scale / ((1.0 - c.rho_node) * c.cscale);
+  double *urow = P.gamma + (size_t)c.start * P.ld;
+  for (uint32_t z = warp; z < P.k; z += nwarps) {
+    double s = 0.0, l = 0.0;
+    for (uint32_t b = lane; b < active; b += 32u) {
+      s += P.partS[(size_t)b * cap + z];
+      l += P.partL[(size_t)b * cap + z];
     }
-  }
-  if (!P.nolambda) {
-    for (uint32_t z = threadIdx.x; z < P.k; z += blockDim.x) {
-      double s = 0.0;
-      for (uint32_t b = 0; b < P.pair_blocks; ++b) s += P.partL[(size_t)b * cap + z];
-      for (uint32_t t = 0; t < 2; ++t) {
-        const double raw = t == c.type ? s : 0.0;            // phi1*phi2*(t==0 ? y : 1-y)
-        const double ldt = (t == 0 ? P.eta0 : P.eta1) + c.scale * raw;
-        P.lambda[2 * z + t] = (1.0 - c.rho_t) * P.lambda[2 * z + t] + c.rho_t * ldt;
-      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      l += __shfl_xor_sync(0xffffffffu, l, o);
+    }
+    if (lane == 0) {
+      // lazy mode, the start row: u += rho*scale*(sum of its phis) / c'   (eager mode: k_fa2_blend does it)
+      if (P.lazy) urow[z] = fma(coef, s, urow[z]);
+      if (!P.nolambda)
+        for (uint32_t t = 0; t < 2; ++t) {
+          const double raw = t == c.type ? l : 0.0;            // phi1*phi2*(t==0 ? y : 1-y)
+          const double ldt = (t == 0 ? P.eta0 : P.eta1) + c.scale * raw;
+          P.lambda[2 * z + t] = (1.0 - c.rho_t) * P.lambda[2 * z + t] + c.rho_t * ldt;
+        }
     }
   }
   __syncthreads();

@@ -641,15 +641,18 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   // ---- device memory ----
   uint64_t &tot = h->device_bytes;
   const size_t nld = (size_t)n * ld;
+  // persistent grids: no more blocks than keep every lane group busy with a few items (each block ends in a block-wide
+  // reduction of its column sums, which at small sizes would otherwise outweigh the rows it summed)
+  const int64_t node_groups = kThreads / ops.lanes;
   h->blocks_node = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ops.max_blocks_node(h->sms),
-                                                                   ((int64_t)nlocal * ops.lanes + kThreads - 1) / kThreads));
+                                                                   ((int64_t)nlocal + node_groups * 8 - 1) / (node_groups * 8)));
   if (ops.s3_ring)
     h->blocks_s3 = (uint32_t)std::max<int64_t>(
         1, std::min<int64_t>(ops.max_blocks_s3_ring(h->sms, ld),
-                             ((int64_t)nseg3 * ops.s3_lanes + ops.s3_threads - 1) / ops.s3_threads));
+                             ((int64_t)nseg3 * ops.s3_lanes + ops.s3_threads * 4 - 1) / (ops.s3_threads * 4)));
   else
     h->blocks_s3 = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ops.max_blocks_s3(h->sms),
-                                                                   ((int64_t)nseg3 * ops.lanes + kThreads - 1) / kThreads));
+                                                                   ((int64_t)nseg3 * ops.lanes + kThreads * 4 - 1) / (kThreads * 4)));
   if (ops.prepare_phi_ring) ops.prepare_phi_ring();   // (setting the attribute loads the ring kernels too)
   if (ops.prepare_s3_ring) ops.prepare_s3_ring();
   if (ops.preload) ops.preload();
@@ -900,7 +903,7 @@ void launch_s3(svi_ls *h, cudaStream_t st) {
   } else {
     h->ops.s3(P, st, h->blocks_s3);
   }
-  svi::k_reduce_kpart<<<2, 256, 0, st>>>(h->d_kpart, h->blocks_s3, 1, cap3, h->d_kvec + 3 * (size_t)P.ld, P.ld);
+  svi::k_reduce_kpart<<<svi::reduce_kpart_blocks(1, P.ld), 256, 0, st>>>(h->d_kpart, h->blocks_s3, 1, cap3, h->d_kvec + 3 * (size_t)P.ld, P.ld);
 }
 
 }  // namespace
@@ -923,7 +926,7 @@ int svi_ls_phase_node(svi_ls *h) {
   DeviceGuard guard(h->device);
   const Params &P = h->P;
   launch_node(h, h->stream, P.node_begin, P.node_end, 0);
-  svi::k_reduce_kpart<<<4, 256, 0, h->stream>>>(h->d_kpart, h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec,
+  svi::k_reduce_kpart<<<svi::reduce_kpart_blocks(3, P.ld), 256, 0, h->stream>>>(h->d_kpart, h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec,
                                                h->d_kvec, P.ld);
   CK(cudaGetLastError());
   return SVI_OK;
@@ -975,7 +978,7 @@ static int enqueue_step(svi_ls *h, cudaStream_t st, uint32_t iter, int annealing
   if (rc) return rc;
   launch_phi(h, st, st, iter, write_comm, 0, P.nseg_lo, P.nseg_lo, P.nseg);
   launch_node(h, st, P.node_begin, P.node_end, 0);
-  svi::k_reduce_kpart<<<4, 256, 0, st>>>(h->d_kpart, h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec, h->d_kvec, P.ld);
+  svi::k_reduce_kpart<<<svi::reduce_kpart_blocks(3, P.ld), 256, 0, st>>>(h->d_kpart, h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec, h->d_kvec, P.ld);
   launch_s3(h, st);
   h->ops.lambda(P, st, annealing, 1);
   h->ops.refresh(P, st, true);
@@ -1273,7 +1276,7 @@ int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
   if (multi) svi::k_mg_signal<<<1, 32, 0, side>>>(pr, svi::FLAG_M, e);
   smark(1);
   mark(2);
-  svi::k_reduce_kpart<<<4, 256, 0, mn>>>(h->d_kpart, nchunks * h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec, h->d_kvec, ld);
+  svi::k_reduce_kpart<<<svi::reduce_kpart_blocks(3, ld), 256, 0, mn>>>(h->d_kpart, nchunks * h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec, h->d_kvec, ld);
   if (multi) {   // all-reduce of sum, s1, s2 (`sum` feeds the annealing rescale, :541-542)
     svi::k_mg_kx_push<<<1, 256, 0, mn>>>(pr, h->d_kvec, 3 * ld, par, 0, svi::FLAG_KXN, e);
     svi::k_mg_kx_sum<<<1, 256, 0, mn>>>(pr, h->d_kvec, 3 * ld, par, 0, svi::FLAG_KXN, e, h->d_mg_err, h->mg_timeout_ns);

@@ -345,17 +345,23 @@ __global__ void __launch_bounds__(256) k_node(const Params P) {
   block_reduce_columns<G, V>(cs2, smem, out + 2 * CAP);
 }
 
-// fixed-order final reduction of `nvec` column vectors over `nblocks` block partials
-static __global__ void k_reduce_kpart(const double *kpart, uint32_t nblocks, uint32_t nvec, uint32_t cap,
-                               double *kvec, uint32_t ld) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec * ld; i += gridDim.x * blockDim.x) {
-    const uint32_t v = i / ld, c = i % ld;
-    double s = 0.0;
-    if (c < cap)
-      for (uint32_t b = 0; b < nblocks; ++b) s += kpart[((size_t)b * nvec + v) * cap + c];
-    kvec[(size_t)v * ld + c] = s;
-  }
+// fixed-order final reduction of `nvec` column vectors over `nblocks` block partials: one warp per (vector, column);
+// lane l sums the blocks l, l+32, ... in order, then a fixed butterfly -- the same bits on every run, and a serial
+// chain of nblocks/32 instead of nblocks (the block count is ~1000 at small sizes, where this kernel used to cost as
+// much as the sweep it follows)
+static __global__ void __launch_bounds__(256) k_reduce_kpart(const double *kpart, uint32_t nblocks, uint32_t nvec,
+                                                             uint32_t cap, double *kvec, uint32_t ld) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (w >= nvec * ld) return;
+  const uint32_t v = w / ld, c = w % ld;
+  double s = 0.0;
+  if (c < cap)
+    for (uint32_t b = lane; b < nblocks; b += 32u) s += kpart[((size_t)b * nvec + v) * cap + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) kvec[(size_t)v * ld + c] = s;
 }
+static inline uint32_t reduce_kpart_blocks(uint32_t nvec, uint32_t ld) { return (nvec * ld * 32u + 255u) / 256u; }
 
 // K3: s3 sweep (src/linksampling.cc:731-746) over the half-edges the shard's nodes own (p = owner, q = other):
 //   s3[k] += mphi[p][k]*mphi[q][k]              both or neither endpoint converged
