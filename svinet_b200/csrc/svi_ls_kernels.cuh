@@ -10,9 +10,11 @@
 // max_k Elogpi[i][:])  once per node per iteration (N*K exps instead of E*K), so an edge costs
 // two multiplies, one group reduction and one FMA per community:
 //     w[k] = (b[p][k] * b[q][k]) * eb[k];   phi[k] = w[k] / sum_k w[k]
-// (b[p]*b[q] first: IEEE multiplication commutes, so both directions of a link see bit-identical
-// phi).  For K > 256 the factors can underflow, and the same kernels run in the log domain
-// (LOGDOM: rows hold Elogpi, one exp per element).
+// (k_phi multiplies b[p]*b[q] first: IEEE multiplication commutes, so both directions of a link see bit-identical
+// phi; the ring sweeps fold eb into the self factor, (b[p]*eb)*b[q], and their two directions may differ in the last
+// bit -- which is why the link-community arg-max is taken ONCE per link, on the owner's side, for both endpoints.)
+// For K > 256 the factors can underflow, and the same kernels run in the log domain (LOGDOM: rows hold Elogpi, one
+// exp per element).
 //
 // Thread mapping: a GROUP of G lanes (G = 2..32, a power of two) owns one work item (a segment
 // of <= seg_len neighbours of one node, or one node row); each lane holds V double2 = 2V
@@ -104,6 +106,17 @@ __device__ __forceinline__ void st_row2(double *row, uint32_t c, uint32_t ld, do
 __device__ __forceinline__ double digamma_pos(double x) {
   double acc = 0.0;
   if (!(x > 0.0)) return CUDART_NAN;
+  // recurrence psi(x) = psi(x+1) - 1/x up to x >= 10.  Late in a run most of gamma sits near alpha << 1, i.e. ten
+  // steps per element, and an FP64 division is ~12 instructions: four steps are taken at once as ONE division,
+  //   1/a + 1/b + 1/c + 1/d = ((a+b)cd + (c+d)ab) / (ab cd)      (a..d = x..x+3; products < 1e4, no range issue)
+  // -- 4 divisions instead of 10 for x < 1, the same end point x + n as the step-by-step loop (the refresh kernel:
+  // 4.6 -> see DESIGN.md section 4 at config 4 once the state has concentrated).
+  while (x < 7.0) {
+    const double a = x, b = x + 1.0, c = x + 2.0, d = x + 3.0;
+    const double ab = a * b, cd = c * d;
+    acc -= fma(a + b, cd, (c + d) * ab) / (ab * cd);
+    x += 4.0;
+  }
   while (x < 10.0) { acc -= 1.0 / x; x += 1.0; }
   const double inv = 1.0 / x, inv2 = inv * inv;
   const double series = inv2 * (1.0 / 12.0 - inv2 * (1.0 / 120.0 - inv2 * (1.0 / 252.0 - inv2 * (1.0 / 240.0
@@ -120,7 +133,7 @@ __device__ __forceinline__ double digamma_pos(double x) {
 template <int G, int V, bool LOGDOM, bool SPARSE, bool COMM>
 __global__ void __launch_bounds__(256) k_phi(const Params P, const uint32_t seg_first, const uint32_t seg_end,
                                              const uint32_t seg_first2, const uint32_t seg_end2, const uint32_t publish) {
-  constexpr int U = (V <= 4) ? 2 : 1;   // neighbour rows in flight per group
+  constexpr int U = V == 1 ? 4 : (V <= 4) ? 2 : 1;   // neighbour rows in flight per group (small rows: latency, not bytes)
   const unsigned mask = group_mask<G>();
   const uint32_t lane = threadIdx.x & (G - 1);
   // two ranges of the segment table in one launch (a chunk of nodes: its "lo" segments and its "up" segments)
@@ -371,7 +384,7 @@ template <int G, int V>
 __global__ void __launch_bounds__(256) k_s3(const Params P) {
   extern __shared__ double smem[];
   constexpr int CAP = 2 * G * V;
-  constexpr int U = (V <= 4) ? 2 : 1;
+  constexpr int U = V == 1 ? 4 : (V <= 4) ? 2 : 1;
   const uint32_t lane = threadIdx.x & (G - 1);
   const uint32_t ggid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const uint32_t ngroups = gridDim.x * blockDim.x / G;

@@ -19,13 +19,14 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, n, k, links, gamma0, sched, conv0, out, overlap=True):
+def _worker(rank, world, port, n, k, links, gamma0, sched, conv0, out, overlap=True, ones=None):
     sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from numpy_shard_engine import NumpyShardEngine
     from svinet_b200.sharded import ShardedLinkSampling
-    sh = ShardedLinkSampling(n, k, links, rank=rank, world=world, engine_factory=NumpyShardEngine, overlap=overlap)
+    sh = ShardedLinkSampling(n, k, links, rank=rank, world=world, engine_factory=NumpyShardEngine, overlap=overlap,
+                             ones=ones)
     sh.set_state(gamma0, np.ones((k, 2)))
     sh.eng.conv[:] = conv0
     res = []
@@ -55,7 +56,10 @@ def test_sharded_equals_oracle_over_gloo(world, overlap, tmp_path):
 
     st = orc.State.alloc(n, k, links.shape[0])
     c = st.c
-    c.alpha, c.eta0, c.eta1, c.ones = 1.0 / k, 1.0, 1.0, links.shape[0]
+    # `ones` (numerator of the annealing rescale, linksampling.cc:541-542) counts ALL links of the network, held-out ones
+    # included: larger than the training-link count whenever a validation set is held out
+    ones = links.shape[0] + (37 if world == 3 else 0)
+    c.alpha, c.eta0, c.eta1, c.ones = 1.0 / k, 1.0, 1.0, ones
     st.arr("links")[:] = links
     tl = np.zeros(n); np.add.at(tl, links.ravel().astype(np.int64), 2.0)
     st.arr("tl")[:] = tl
@@ -65,7 +69,7 @@ def test_sharded_equals_oracle_over_gloo(world, overlap, tmp_path):
     st.refresh_expectations()
 
     out = str(tmp_path / "res.pt")
-    mp.spawn(_worker, args=(world, _free_port(), n, k, links, gamma0, sched, conv0, out, overlap), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, k, links, gamma0, sched, conv0, out, overlap, ones), nprocs=world, join=True)
     got = torch.load(out, weights_only=False)
     bounds = got["bounds"]
     assert bounds[0] == 0 and bounds[-1] == n and np.all(np.diff(bounds) > 0)
