@@ -619,6 +619,59 @@ static int validation_likelihood(orc_model *m) {
 }
 
 /* LinkSampling::LinkSampling, linksampling.cc:5-155 */
+/* LinkSampling::init_gamma_external, linksampling.cc:404-452, fed by Network::load_init_communities,
+ * network.cc:374-437 (one community per line: external node ids).  For every node p and every adjacency entry of p
+ * the SAME vector phi[k] = alpha + [k in communities(p)] * n / |communities(p)|, normalised by its plain sum
+ * (matrix.hh:341-346), is added to row p of gamma, which starts at alpha.  No RNG use. */
+static int init_gamma_external(orc_model *m, const char *path) {
+  const orc_graph *g = m->g;
+  orc_state *s = m->s;
+  const uint32_t n = s->n, k = s->k;
+  FILE *f = fopen(path, "r");
+  if (!f) return -1;
+  uint32_t *cnt = (uint32_t *)calloc(n ? n : 1, sizeof(uint32_t));
+  uint32_t *mem = NULL;                 /* (node, community) pairs in file order */
+  size_t nmem = 0, cap = 0;
+  char *line = NULL;
+  size_t lcap = 0;
+  uint32_t cid = 0;
+  while (getline(&line, &lcap, f) > 0) {
+    char *p = line, *e = NULL;
+    int any = 0;
+    for (;; p = e) {
+      long u = strtol(p, &e, 10);
+      if (p == e) break;
+      uint32_t seq = n;
+      for (uint32_t i = 0; i < g->n_arg; ++i) if (g->seq2id[i] == (uint32_t)u) { seq = i; break; }
+      if (seq < n) {
+        if (nmem == cap) { cap = cap ? 2 * cap : 256; mem = (uint32_t *)realloc(mem, 2 * cap * sizeof(uint32_t)); }
+        mem[2 * nmem] = seq; mem[2 * nmem + 1] = cid; nmem++;
+        cnt[seq]++;
+      }
+      any = 1;
+    }
+    if (any) cid++;
+  }
+  free(line);
+  fclose(f);
+  double *phi = (double *)calloc(k ? k : 1, sizeof(double));
+  for (uint32_t p = 0; p < n; ++p) {
+    double *row = s->gamma + (size_t)p * k;
+    for (uint32_t c = 0; c < k; ++c) row[c] = s->alpha;
+    for (uint32_t c = 0; c < k; ++c) phi[c] = s->alpha;
+    for (size_t j = 0; j < nmem; ++j)
+      if (mem[2 * j] == p && mem[2 * j + 1] < k) phi[mem[2 * j + 1]] += (double)n / cnt[p];
+    double sum = .0;
+    for (uint32_t c = 0; c < k; ++c) sum += phi[c];
+    for (uint32_t c = 0; c < k; ++c) phi[c] = phi[c] / sum;
+    const uint64_t deg = g->adj_off[p + 1] - g->adj_off[p];
+    for (uint64_t r = 0; r < deg; ++r)
+      for (uint32_t c = 0; c < k; ++c) row[c] += phi[c];
+  }
+  free(phi); free(mem); free(cnt);
+  return 0;
+}
+
 orc_model *orc_model_create(const orc_graph *g, const orc_options *o) {
   orc_model *m = (orc_model *)calloc(1, sizeof(orc_model));
   m->g = g; m->o = *o;
@@ -637,7 +690,11 @@ orc_model *orc_model_create(const orc_graph *g, const orc_options *o) {
   if (o->seed) orc_rng_seed(&m->rng, (unsigned long)o->seed);   /* :74-75 */
   int s1 = (int)(o->heldout_ratio * g->ones);          /* init_validation, :167 */
   set_validation_sample(m, s1);
-  init_gamma2(m);                                      /* :117 */
+  if (o->init_communities) {                           /* :113-116 */
+    if (init_gamma_external(m, o->init_communities)) { orc_model_free(m); return NULL; }
+  } else {
+    init_gamma2(m);                                    /* :117 */
+  }
   for (size_t i = 0; i < (size_t)n * k; ++i) s->gammanext[i] = s->alpha;
   for (uint32_t c = 0; c < k; ++c) {                   /* init_lambda, :364-372 */
     s->lambda[2 * c] = s->lambdanext[2 * c] = s->eta0;

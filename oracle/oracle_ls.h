@@ -96,6 +96,7 @@ typedef struct orc_options {
   uint32_t reportfreq;         /* 1 for -link-sampling (main.cc:149-153)       */
   double   eta0, eta1;         /* 1,1 for -eta-type uniform (network.cc:238)   */
   double   epsilon;            /* 1e-30 (env.hh:395)                           */
+  const char *init_communities;/* -init-communities <file> (NULL = init_gamma2)  */
 } orc_options;
 
 void       orc_options_default(orc_options *o, uint32_t k);

@@ -57,7 +57,7 @@ struct Ops {
   void (*lambda)(const Params &, cudaStream_t, int annealing, int update);
   void (*refresh)(const Params &, cudaStream_t, bool from_gacc);
   void (*heldout)(const Params &, cudaStream_t, uint64_t, const uint32_t *, const uint32_t *, const uint8_t *,
-                  double, double *, const svi::Peers *peer_rows);
+                  double, double *, unsigned long long *bad, const svi::Peers *peer_rows);
   int (*max_blocks_node)(int sms);
   int (*max_blocks_s3)(int sms);
   int lanes, vec, logdom;
@@ -117,11 +117,11 @@ struct Tile {
     else svi::k_refresh<G, V, L, false><<<blocks, kThreads, 0, st>>>(P);
   }
   static void heldout(const Params &P, cudaStream_t st, uint64_t np, const uint32_t *p, const uint32_t *q,
-                      const uint8_t *y, double eps, double *out, const svi::Peers *peer_rows) {
+                      const uint8_t *y, double eps, double *out, unsigned long long *bad, const svi::Peers *peer_rows) {
     if (!np) return;
     const uint32_t blocks = (uint32_t)((np * G + kThreads - 1) / kThreads);
-    if (peer_rows) svi::k_heldout<G, V, svi::Peers><<<blocks, kThreads, 0, st>>>(P, *peer_rows, np, p, q, y, eps, out);
-    else svi::k_heldout<G, V, svi::LocalRows><<<blocks, kThreads, 0, st>>>(P, svi::LocalRows{P.gamma}, np, p, q, y, eps, out);
+    if (peer_rows) svi::k_heldout<G, V, svi::Peers><<<blocks, kThreads, 0, st>>>(P, *peer_rows, np, p, q, y, eps, out, bad);
+    else svi::k_heldout<G, V, svi::LocalRows><<<blocks, kThreads, 0, st>>>(P, svi::LocalRows{P.gamma}, np, p, q, y, eps, out, bad);
   }
   static int occ(const void *fn, int sms) {
     int per_sm = 0;
@@ -1403,27 +1403,29 @@ int svi_ls_heldout(svi_ls *h, uint64_t npairs, const uint32_t *p, const uint32_t
   if (!h || (npairs && (!p || !q || !y || !loglik))) return fail(SVI_ERR_INVALID, "svi_ls_heldout: null argument");
   if (!npairs) return SVI_OK;
   DeviceGuard guard(h->device);
-  for (uint64_t i = 0; i < npairs; ++i)
-    if (p[i] >= h->P.n || q[i] >= h->P.n) return fail(SVI_ERR_INVALID, "svi_ls_heldout: pair %llu out of range",
-                                                      (unsigned long long)i);
   // staging: [p | q] as uint32, y as bytes, out as double -- carve from one scratch allocation
-  const size_t bytes = npairs * (2 * sizeof(uint32_t) + sizeof(double)) + ((npairs + 7) & ~(size_t)7);
+  const size_t bytes = npairs * (2 * sizeof(uint32_t) + sizeof(double)) + ((npairs + 7) & ~(size_t)7) + 8;
   int rc = ensure_stage(h, (bytes + sizeof(double) - 1) / sizeof(double));
   if (rc) return rc;
   double *d_out = h->d_stage;
   uint32_t *d_p = reinterpret_cast<uint32_t *>(d_out + npairs);
   uint32_t *d_q = d_p + npairs;
   uint8_t *d_y = reinterpret_cast<uint8_t *>(d_q + npairs);
+  unsigned long long *d_bad = reinterpret_cast<unsigned long long *>(d_y + ((npairs + 7) & ~(size_t)7));
+  CK(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), h->stream));
   // sharded: the rows of other shards are read from their arenas (peer loads), unless gamma is replicated
   const bool peer_rows = h->mg && h->peers.world > 1 && !h->share_gamma;
   if (h->share_gamma) mg_await_rows(h);
   CK(cudaMemcpyAsync(d_p, p, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(d_q, q, npairs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(d_y, y, npairs, cudaMemcpyHostToDevice, h->stream));
-  h->ops.heldout(h->P, h->stream, npairs, d_p, d_q, d_y, epsilon, d_out, peer_rows ? &h->peers : nullptr);
+  h->ops.heldout(h->P, h->stream, npairs, d_p, d_q, d_y, epsilon, d_out, d_bad, peer_rows ? &h->peers : nullptr);
   CK(cudaGetLastError());
+  unsigned long long bad = 0;
   CK(cudaMemcpyAsync(loglik, d_out, npairs * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (bad) return fail(SVI_ERR_INVALID, "svi_ls_heldout: pair %llu out of range", bad - 1ull);
   return SVI_OK;
 }
 

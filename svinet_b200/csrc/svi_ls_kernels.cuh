@@ -610,12 +610,19 @@ struct LocalRows {
 template <int G, int V, class ROWS>
 __global__ void __launch_bounds__(256) k_heldout(const Params P, const ROWS rows, uint64_t npairs, const uint32_t *pp,
                                                  const uint32_t *qq, const uint8_t *yy, double epsilon,
-                                                 double *out) {
+                                                 double *out, unsigned long long *bad) {
   const unsigned mask = group_mask<G>();
   const uint32_t lane = threadIdx.x & (G - 1);
   const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
   if (i >= npairs) return;
   const uint32_t p = pp[i], q = qq[i];
+  if (p >= P.n || q >= P.n) {   // the pair list is validated here, not in a host loop: *bad = 1 + index of one bad pair
+    if (lane == 0) {
+      atomicMax(bad, (unsigned long long)i + 1ull);
+      out[i] = CUDART_NAN;
+    }
+    return;
+  }
   const int y = yy[i];
   double2 gp[V], gq[V];
   double sp = 0.0, sq = 0.0;

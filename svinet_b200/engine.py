@@ -260,13 +260,16 @@ class LinkSamplingEngine:
         _check(self.L, self.L.svi_ls_mg_timing(self.h, int(enable), _ptr(ms), C.byref(cnt)))
         return dict(zip(self.MG_PHASES, [float(x) for x in ms])), cnt.value
 
-    def membership_rows(self, first, count):
-        bits = np.empty((count, self.words), dtype=np.uint32)
+    def membership_rows(self, first, count, out=None):
+        bits = np.empty((count, self.words), dtype=np.uint32) if out is None else out
+        assert bits.shape == (count, self.words) and bits.dtype == np.uint32 and bits.flags.c_contiguous
         _check(self.L, self.L.svi_ls_get_membership_rows(self.h, first, count, _ptr(bits)))
         return bits
 
-    def membership_bits(self):
-        bits = np.empty((self.n, self.words), dtype=np.uint32)
+    def membership_bits(self, out=None):
+        """out: optional caller-owned [n, words] uint32 array (e.g. a view of pinned memory)"""
+        bits = np.empty((self.n, self.words), dtype=np.uint32) if out is None else out
+        assert bits.shape == (self.n, self.words) and bits.dtype == np.uint32 and bits.flags.c_contiguous
         _check(self.L, self.L.svi_ls_get_membership(self.h, _ptr(bits)))
         return bits
 
@@ -276,11 +279,12 @@ class LinkSamplingEngine:
         cols = np.arange(self.k)
         return ((bits[:, cols // 32] >> (cols % 32).astype(np.uint32)) & 1).astype(np.uint8)
 
-    def heldout(self, p, q, y, epsilon=1e-30):
+    def heldout(self, p, q, y, epsilon=1e-30, out=None):
         p = np.ascontiguousarray(p, dtype=np.uint32)
         q = np.ascontiguousarray(q, dtype=np.uint32)
         y = np.ascontiguousarray(y, dtype=np.uint8)
-        out = np.empty(p.shape[0], dtype=np.float64)
+        out = np.empty(p.shape[0], dtype=np.float64) if out is None else out
+        assert out.shape == (p.shape[0],) and out.dtype == np.float64
         _check(self.L, self.L.svi_ls_heldout(self.h, p.shape[0], _ptr(p), _ptr(q), _ptr(y), epsilon, _ptr(out)))
         return out
 

@@ -42,7 +42,8 @@ class OrcState(C.Structure):
 class OrcOptions(C.Structure):
     _fields_ = [("k", C.c_uint32), ("seed", C.c_double), ("heldout_ratio", C.c_double),
                 ("accuracy", C.c_int), ("max_iterations", C.c_uint32), ("use_validation_stop", C.c_int),
-                ("reportfreq", C.c_uint32), ("eta0", C.c_double), ("eta1", C.c_double), ("epsilon", C.c_double)]
+                ("reportfreq", C.c_uint32), ("eta0", C.c_double), ("eta1", C.c_double), ("epsilon", C.c_double),
+                ("init_communities", C.c_char_p)]
 
 
 class OrcFa2Options(C.Structure):

@@ -14,7 +14,7 @@ import oracle_py as orc
 from golden_util import MANIFEST, Scratch, compare_numeric_text, golden_text, input_path
 
 
-def _flags_to_opts(flags):
+def _flags_to_opts(flags, scratch=None):
     o = {}
     i = 0
     while i < len(flags):
@@ -27,6 +27,8 @@ def _flags_to_opts(flags):
             o["seed"] = float(flags[i + 1]); i += 1
         elif f == "-accuracy":
             o["accuracy"] = 1
+        elif f == "-init-communities":              # linksampling.cc:113-116
+            o["init_communities"] = input_path(flags[i + 1], scratch).encode(); i += 1
         elif f == "-eta-type":                      # network.cc:233-250
             o["eta0"], o["eta1"] = {"uniform": (1.0, 1.0), "sparse": (0.97, 6.33), "dense": (4700.59, 0.77)}[flags[i + 1]]
             i += 1
@@ -45,7 +47,7 @@ def _run_case(case):
     ent = MANIFEST[case]
     with Scratch() as d:
         g = orc.Graph.read(input_path(ent["input"], d), ent["n"])
-        m = orc.Model(g, ent["k"], **_flags_to_opts(ent["flags"]))
+        m = orc.Model(g, ent["k"], **_flags_to_opts(ent["flags"], d))
         m.run()
         assert m.stopped
         out = os.path.join(d, "out")
