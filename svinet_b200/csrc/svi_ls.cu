@@ -1119,7 +1119,7 @@ static int mg_finish_attach(svi_ls *h, uint32_t world, uint32_t rank, const uint
   CK(cudaStreamSynchronize(h->side));
   h->epoch = 0;
   h->mg = true;
-  h->partition_every_sweep = world > 1;
+  h->partition_every_sweep = false;   // the shards all-reduce their "newly converged" flags (svi_ls_mg_step)
   const char *te = getenv("SVI_LS_MG_TIMEOUT_S");
   if (te && atof(te) > 0) h->mg_timeout_ns = (uint64_t)(atof(te) * 1e9);
   return SVI_OK;
@@ -1278,8 +1278,8 @@ int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
   mark(2);
   svi::k_reduce_kpart<<<svi::reduce_kpart_blocks(3, ld), 256, 0, mn>>>(h->d_kpart, nchunks * h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec, h->d_kvec, ld);
   if (multi) {   // all-reduce of sum, s1, s2 (`sum` feeds the annealing rescale, :541-542)
-    svi::k_mg_kx_push<<<1, 256, 0, mn>>>(pr, h->d_kvec, 3 * ld, par, 0, svi::FLAG_KXN, e);
-    svi::k_mg_kx_sum<<<1, 256, 0, mn>>>(pr, h->d_kvec, 3 * ld, par, 0, svi::FLAG_KXN, e, h->d_mg_err, h->mg_timeout_ns);
+    svi::k_mg_kx_push<<<1, 256, 0, mn>>>(pr, h->d_kvec, 3 * ld, par, 0, svi::FLAG_KXN, e, nullptr);
+    svi::k_mg_kx_sum<<<1, 256, 0, mn>>>(pr, h->d_kvec, 3 * ld, par, 0, svi::FLAG_KXN, e, h->d_mg_err, h->mg_timeout_ns, nullptr);
   }
   if (multi && write_comm && P.nseg) {   // membership words of our rows: merge the peers' replicas (their sweeps are done)
     const size_t first = (size_t)P.node_begin * P.words, cnt = (size_t)(P.node_end - P.node_begin) * P.words;
@@ -1311,9 +1311,11 @@ int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
   launch_s3(h, mn);
   mark(6);
   if (multi) {
-    svi::k_mg_kx_push<<<1, 256, 0, mn>>>(pr, h->d_kvec + 3 * (size_t)ld, ld, par, 1, svi::FLAG_KXS, e);
+    // the shards' "a node newly converged" flags (set by this iteration's refresh) ride along: the next iteration
+    // re-partitions the neighbour lists only if some shard saw one
+    svi::k_mg_kx_push<<<1, 256, 0, mn>>>(pr, h->d_kvec + 3 * (size_t)ld, ld, par, 1, svi::FLAG_KXS, e, h->d_conv_dirty);
     svi::k_mg_kx_sum<<<1, 256, 0, mn>>>(pr, h->d_kvec + 3 * (size_t)ld, ld, par, 1, svi::FLAG_KXS, e, h->d_mg_err,
-                                       h->mg_timeout_ns);
+                                       h->mg_timeout_ns, h->d_conv_dirty);
   }
   h->ops.lambda(P, mn, annealing, 1);
   flip_converged(h);

@@ -110,12 +110,15 @@ static __global__ void __launch_bounds__(256) k_mg_or_rows(const Peers pr, const
 
 // all-reduce, first half: our `count` doubles (count <= kx_stride) go into slot [parity][which][rank] of every
 // shard's arena (our own included), then the flag `kind` is raised.  One block.
+//   extra (may be null): one more value rides along at index `count` -- the shard's "a node newly converged" flag
 static __global__ void k_mg_kx_push(const Peers pr, const double *src, const uint32_t count, const uint32_t parity,
-                                    const uint32_t which, const uint32_t kind, const uint32_t epoch) {
+                                    const uint32_t which, const uint32_t kind, const uint32_t epoch,
+                                    const uint32_t *extra) {
   const size_t slot = ((size_t)(parity * 2u + which) * kMaxWorld + pr.rank) * pr.kx_stride;
   for (uint32_t t = 0; t < pr.world; ++t) {
     double *dst = reinterpret_cast<double *>(pr.arena[t] + pr.kx_off) + slot;
     for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+    if (extra && threadIdx.x == 0) dst[count] = (double)*extra;
   }
   __threadfence_system();
   __syncthreads();
@@ -126,9 +129,10 @@ static __global__ void k_mg_kx_push(const Peers pr, const double *src, const uin
 
 // all-reduce, second half: wait for every shard's slot, then sum them in rank order (the same order on every
 // shard: the result is bit-identical everywhere).  One block.
+//   extra_out (may be null): receives 1 if any shard's extra value was non-zero
 static __global__ void k_mg_kx_sum(const Peers pr, double *dst, const uint32_t count, const uint32_t parity,
                                    const uint32_t which, const uint32_t kind, const uint32_t epoch, uint32_t *err,
-                                   const uint64_t timeout_ns) {
+                                   const uint64_t timeout_ns, uint32_t *extra_out) {
   mg_wait_flags(pr, kind, epoch, err, timeout_ns);
   __syncthreads();
   const double *base = reinterpret_cast<const double *>(pr.arena[pr.rank] + pr.kx_off) +
@@ -137,6 +141,11 @@ static __global__ void k_mg_kx_sum(const Peers pr, double *dst, const uint32_t c
     double s = 0.0;
     for (uint32_t r = 0; r < pr.world; ++r) s += __ldcg(base + (size_t)r * pr.kx_stride + i);
     dst[i] = s;
+  }
+  if (extra_out && threadIdx.x == 0) {
+    double any = 0.0;
+    for (uint32_t r = 0; r < pr.world; ++r) any += __ldcg(base + (size_t)r * pr.kx_stride + count);
+    *extra_out = any > 0.0 ? 1u : 0u;
   }
 }
 

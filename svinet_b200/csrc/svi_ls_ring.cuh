@@ -392,24 +392,33 @@ static __global__ void __launch_bounds__(256) k_partition(const Params P, const 
   const uint32_t nwarps = gridDim.x * 8u;
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t *col = const_cast<uint32_t *>(P.col);
+  uint32_t *st = stage[w];
   for (uint32_t seg = blockIdx.x * 8u + w; seg < P.nseg; seg += nwarps) {
     const uint32_t beg = P.seg_beg[seg], cnt = P.seg_cnt[seg];
-    uint32_t nnc = 0;
-    for (uint32_t i0 = 0; i0 < cnt; i0 += 32u) {
-      const bool in = i0 + lane < cnt;
-      const uint32_t q = in ? col[beg + i0 + lane] : 0u;
-      if (in) stage[w][i0 + lane] = q;
-      nnc += __popc(__ballot_sync(0xffffffffu, in && P.conv[q] == 0u));
+    // three passes with INDEPENDENT loads inside each (the first version chained id -> flag -> ballot per 32
+    // neighbours and was latency-bound: ~2.5 ms at config 4 whenever a node had converged): ids, then their flags
+    // (kept in bit 31 of the staged id: node ids are < 2^31), then the scatter
+    for (uint32_t i = lane; i < cnt; i += 32u) st[i] = col[beg + i];
+    __syncwarp();
+    uint32_t mine = 0;
+    for (uint32_t i = lane; i < cnt; i += 32u) {
+      const uint32_t q = st[i];
+      const uint32_t nc = P.conv[q] == 0u ? 1u : 0u;
+      st[i] = q | (nc << 31);
+      mine += nc;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    const uint32_t nnc = mine;
     __syncwarp();
     if (nnc != P.seg_nnc[seg] || force) {   // (a segment none of whose neighbours changed keeps its order)
       uint32_t a = 0, b = nnc;
       for (uint32_t i0 = 0; i0 < cnt; i0 += 32u) {
         const bool in = i0 + lane < cnt;
-        const uint32_t q = in ? stage[w][i0 + lane] : 0u;
-        const bool nc = in && P.conv[q] == 0u;
+        const uint32_t v = in ? st[i0 + lane] : 0u;
+        const bool nc = in && (v >> 31);
         const uint32_t mn = __ballot_sync(0xffffffffu, nc), mc = __ballot_sync(0xffffffffu, in && !nc);
-        if (in) col[beg + (nc ? a + __popc(mn & lt) : b + __popc(mc & lt))] = q;
+        if (in) col[beg + (nc ? a + __popc(mn & lt) : b + __popc(mc & lt))] = v & 0x7fffffffu;
         a += __popc(mn);
         b += __popc(mc);
       }
