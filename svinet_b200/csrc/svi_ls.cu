@@ -385,6 +385,11 @@ struct svi_ls {
   cudaGraphExec_t graphs[16] = {};
   cudaStream_t cap = nullptr;
   bool use_graph = true;
+  // the refresh (FP64-bound: digamma, exp) beside the s3 sweep (HBM-bound, 27 % issue utilisation) on a second stream;
+  // the sweep then runs with one block per SM fewer so that a refresh block fits next to it
+  bool overlap_refresh = false;
+  cudaStream_t rf = nullptr, cap_rf = nullptr;
+  cudaEvent_t ev_fork_rf = nullptr, ev_join_rf = nullptr;
   // optional per-phase timing of svi_ls_mg_step (svi_ls_mg_timing): events on the main stream, ring of steps
   static constexpr int kTimedSteps = 32, kMarks = 9, kSideMarks = 4;
   bool timing = false;
@@ -426,6 +431,10 @@ void free_all(svi_ls *h) {
       if (ev) cudaEventDestroy(ev);
   for (cudaGraphExec_t g : h->graphs)
     if (g) cudaGraphExecDestroy(g);
+  if (h->rf) cudaStreamDestroy(h->rf);
+  if (h->cap_rf) cudaStreamDestroy(h->cap_rf);
+  if (h->ev_fork_rf) cudaEventDestroy(h->ev_fork_rf);
+  if (h->ev_join_rf) cudaEventDestroy(h->ev_join_rf);
   if (h->cap) cudaStreamDestroy(h->cap);
   for (cudaStream_t st : h->fan)
     if (st) cudaStreamDestroy(st);
@@ -653,6 +662,8 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   else
     h->blocks_s3 = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ops.max_blocks_s3(h->sms),
                                                                    ((int64_t)nseg3 * ops.lanes + kThreads * 4 - 1) / (kThreads * 4)));
+  if (const char *sb = getenv("SVI_LS_S3_BLOCKS_PER_SM"))
+    if (atoi(sb) > 0) h->blocks_s3 = std::min<uint32_t>(h->blocks_s3, (uint32_t)atoi(sb) * (uint32_t)h->sms);
   if (ops.prepare_phi_ring) ops.prepare_phi_ring();   // (setting the attribute loads the ring kernels too)
   if (ops.prepare_s3_ring) ops.prepare_s3_ring();
   if (ops.preload) ops.preload();
@@ -729,6 +740,13 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   h->nlo = std::move(nlo);
   h->nup = std::move(nup);
   if (const char *ng = getenv("SVI_LS_NO_GRAPH")) h->use_graph = !(ng[0] == '1');
+  if (const char *ov = getenv("SVI_LS_OVERLAP_REFRESH")) h->overlap_refresh = ov[0] == '1';
+  if (h->overlap_refresh) {
+    if (cudaStreamCreateWithFlags(&h->rf, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork_rf, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join_rf, cudaEventDisableTiming) != cudaSuccess)
+      h->overlap_refresh = false;
+  }
   h->he_prefix.assign(nlocal + 1, 0);
   for (uint32_t v = 0; v < nlocal; ++v) h->he_prefix[v + 1] = h->he_prefix[v] + deg_lo[v] + deg_up[v];
   *out = h;
@@ -979,9 +997,23 @@ static int enqueue_step(svi_ls *h, cudaStream_t st, uint32_t iter, int annealing
   launch_phi(h, st, st, iter, write_comm, 0, P.nseg_lo, P.nseg_lo, P.nseg);
   launch_node(h, st, P.node_begin, P.node_end, 0);
   svi::k_reduce_kpart<<<svi::reduce_kpart_blocks(3, P.ld), 256, 0, st>>>(h->d_kpart, h->blocks_node, 3, 2 * h->ops.lanes * h->ops.vec, h->d_kvec, P.ld);
-  launch_s3(h, st);
-  h->ops.lambda(P, st, annealing, 1);
-  h->ops.refresh(P, st, true);
+  if (h->overlap_refresh) {
+    // fork: rescale + refresh (needs `sum` only; writes gamma, b, conv[cur^1], masks) on the second stream, the s3
+    // sweep (reads mphi, conv[cur]) on this one; join before lambda
+    cudaStream_t rf = st == h->cap ? h->cap_rf : h->rf;
+    CK(cudaEventRecord(h->ev_fork_rf, st));
+    CK(cudaStreamWaitEvent(rf, h->ev_fork_rf, 0));
+    svi::k_scale<<<1, 256, 0, rf>>>(P, annealing);
+    h->ops.refresh(P, rf, true);
+    CK(cudaEventRecord(h->ev_join_rf, rf));
+    launch_s3(h, st);
+    CK(cudaStreamWaitEvent(st, h->ev_join_rf, 0));
+    h->ops.lambda(P, st, annealing, 1);
+  } else {
+    launch_s3(h, st);
+    h->ops.lambda(P, st, annealing, 1);
+    h->ops.refresh(P, st, true);
+  }
   CK(cudaGetLastError());
   return SVI_OK;
 }
@@ -999,6 +1031,7 @@ int svi_ls_step(svi_ls *h, uint32_t iter, int annealing, int write_comm) {
   const int key = (sparse ? 1 : 0) | (write_comm ? 2 : 0) | (annealing ? 4 : 0) | (h->cur ? 8 : 0);
   if (!h->graphs[key]) {
     if (!h->cap) CK(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
+    if (h->overlap_refresh && !h->cap_rf) CK(cudaStreamCreateWithFlags(&h->cap_rf, cudaStreamNonBlocking));
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal));
     rc = enqueue_step(h, h->cap, sparse ? 1001u : 0u, annealing, write_comm);
