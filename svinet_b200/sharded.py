@@ -301,8 +301,10 @@ class ShardedLinkSampling:
         import time
         hp, hq, hy = heldout if heldout is not None else (np.zeros(0, np.uint32),) * 2 + (np.zeros(0, np.uint8),)
         if self.exchange == "peer":
-            # every pair is evaluated by the shard that owns its first endpoint: only the other row is a peer load
-            sl = (np.searchsorted(self.bounds, hp, side="right") - 1) == self.rank
+            # every pair is evaluated by a shard that owns one of its endpoints (which one: the parity rule of the s3
+            # ownership, so that the pairs spread evenly): only the other row is a peer load
+            key = np.where(((hp ^ hq) & 1) == 1, hp, hq)
+            sl = (np.searchsorted(self.bounds, key, side="right") - 1) == self.rank
         else:
             sl = slice(self.rank, None, self.world)
         hp, hq, hy = np.ascontiguousarray(hp[sl]), np.ascontiguousarray(hq[sl]), np.ascontiguousarray(hy[sl])
@@ -333,7 +335,7 @@ class ShardedLinkSampling:
                 "h2d_bytes_per_step": int(hp.nbytes + hq.nbytes + hy.nbytes),
                 "d2h_bytes_per_step": int(ll.nbytes + bits.nbytes),
                 "what": ("per rank and iteration: svi_ls_mg_step (peer-memory exchanges) + "
-                         "svi_ls_heldout on the pairs whose first endpoint the rank owns (host in/out; the other row is a "
+                         "svi_ls_heldout on the pairs one of whose endpoints the rank owns (host in/out; the other row is a "
                          "peer load) + svi_ls_get_membership_rows of the rank's own block (host bits)") if self.exchange == "peer" else
                         ("per rank and iteration: sharded step (NCCL exchanges) + gamma row all-gather + "
                          "svi_ls_heldout on 1/world of the pairs (host in/out) + svi_ls_get_membership (host bits)")}
