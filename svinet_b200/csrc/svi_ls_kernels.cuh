@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(256) k_s3(const Params P) {
   extern __shared__ double smem[];
   constexpr int CAP = 2 * G * V;
   constexpr int U = V == 1 ? 4 : (V <= 4) ? 2 : 1;
+  const unsigned mask = group_mask<G>();
   const uint32_t lane = threadIdx.x & (G - 1);
   const uint32_t ggid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const uint32_t ngroups = gridDim.x * blockDim.x / G;
@@ -404,14 +405,22 @@ __global__ void __launch_bounds__(256) k_s3(const Params P) {
 #pragma unroll
     for (int j = 0; j < V; ++j) t[j] = make_double2(0.0, 0.0);
     double one_hot = 0.0;       // shortcut mass for column pc-1 (p converged)
-    for (uint32_t j0 = 0; j0 < cnt; j0 += U) {
+    // ids and converged flags of G neighbours at a time, one per lane (coalesced: two dependent loads per G
+    // neighbours instead of two per U), handed out by shuffles.  (The same change in k_phi measured slower.)
+    for (uint32_t c0 = 0; c0 < cnt; c0 += G) {
+     const uint32_t rem = min((uint32_t)G, cnt - c0);
+     const uint32_t qv = lane < rem ? __ldg(P.col + beg + c0 + lane) : p;
+     const uint32_t qcv = lane < rem ? P.conv[qv] : 0u;
+     for (uint32_t j1 = 0; j1 < rem; j1 += U) {
       uint32_t q[U], qc[U];
       bool live[U], full[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        live[u] = j0 + u < cnt;
-        q[u] = live[u] ? __ldg(P.col + beg + j0 + u) : p;
-        qc[u] = live[u] ? P.conv[q[u]] : 0u;
+        const uint32_t idx = j1 + u;
+        live[u] = idx < rem;
+        q[u] = __shfl_sync(mask, qv, min(idx, (uint32_t)G - 1u), G);
+        qc[u] = __shfl_sync(mask, qcv, min(idx, (uint32_t)G - 1u), G);
+        if (!live[u]) { q[u] = p; qc[u] = 0u; }
         full[u] = live[u] && !((pc != 0u) != (qc[u] != 0u));
       }
 #pragma unroll
@@ -438,6 +447,7 @@ __global__ void __launch_bounds__(256) k_s3(const Params P) {
           }
         }
       }
+     }
     }
 #pragma unroll
     for (int j = 0; j < V; ++j) {
