@@ -106,3 +106,90 @@ def test_shards_where_nodes_converge_on_the_way():
         m.close(); g.close()
     sched = [(it, it < 14, 1) for it in range(28)]
     run_sharded_vs_oracle(75, 4, links, gamma, np.zeros(75, dtype=np.uint32), 3, 2, sched, share=False)
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_phase_level_shards_with_caller_side_exchange(overlap):
+    """The phase-level entry points a driver with its own collectives uses (svinet_b200/sharded.py, exchange="nccl"):
+    two shard handles on one GPU, the exchanges done here with plain tensor copies on the buffers of
+    svi_ls_device_buffer -- the same choreography as ShardedLinkSampling.step / _step_overlapped, incl. the
+    double-buffered `converged` pointer -- against the oracle."""
+    import torch
+    from svinet_b200.sharded import cuda_view
+    n, k = 700, 40
+    links = synth.mmsb_links(n, k, 25 * n, seed=77)
+    gamma, _ = synth.random_state(n, k, links, seed=5)
+    rng = np.random.default_rng(1)
+    conv = np.zeros(n, dtype=np.uint32)
+    who = rng.random(n) < 0.25
+    conv[who] = rng.integers(1, k + 1, who.sum())
+    st = oracle_state(n, k, links, gamma, np.ones((k, 2)), conv)
+    bounds = plan_shards(n, links, 2)
+    tl = 2.0 * np.bincount(links.ravel().astype(np.int64), minlength=n).astype(np.float64)
+    engines = [LinkSamplingEngine(n, k, links, tl=tl, node_range=(int(bounds[r]), int(bounds[r + 1])), seg_len=64)
+               for r in range(2)]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ld = engines[0].info()["ld"]
+    words = (k + 31) // 32
+
+    def view(e, name):
+        ptr, _ = e.device_buffer(name)
+        shape, dt = {"exppi": ((n, ld), torch.float64), "mphi": ((n, ld), torch.float64), "gamma": ((n, ld), torch.float64),
+                     "kvec": ((4, ld), torch.float64), "converged": ((n,), torch.int32), "active": ((n,), torch.int32),
+                     "active_bits": ((n, words), torch.int32), "member_bits": ((n, words), torch.int32)}[name]
+        return cuda_view(ptr, shape, dt, dev)
+
+    def allgather(name):                      # every shard's block of `name` into the other handle
+        for r, e in enumerate(engines):
+            e.sync()
+        for r in range(2):
+            nb, ne = int(bounds[r]), int(bounds[r + 1])
+            view(engines[1 - r], name)[nb:ne] = view(engines[r], name)[nb:ne]
+        torch.cuda.synchronize()
+
+    def allreduce(rows):
+        for e in engines:
+            e.sync()
+        tot = view(engines[0], "kvec")[rows].clone() + view(engines[1], "kvec")[rows]
+        for e in engines:
+            view(e, "kvec")[rows] = tot
+        torch.cuda.synchronize()
+
+    for e in engines:
+        e.set_state(st.arr("gamma"), st.arr("lambda_"))
+        e.set_converged(st.arr("converged"))
+    for it, ann, wc in [(0, 1, 0), (1, 1, 1), (2, 0, 1), (3, 1, 1)]:
+        st.step(it, ann, wc)
+        for e in engines:
+            e.phase_phi(it, wc); e.phase_node()
+        allreduce(slice(0, 3))
+        allgather("mphi")
+        if overlap:
+            for e in engines:
+                e.phase_refresh(ann)
+            allgather("exppi"); allgather("converged")
+            for e in engines:
+                e.phase_s3()
+            allreduce(slice(3, 4))
+            for e in engines:
+                e.phase_lambda(ann)
+        else:
+            for e in engines:
+                e.phase_s3()
+            allreduce(slice(3, 4))
+            for e in engines:
+                e.phase_finish(ann)
+            allgather("exppi"); allgather("converged")
+        allgather("gamma")
+        mem = np.zeros((n, k), dtype=np.uint8)
+        for r, e in enumerate(engines):
+            g, lam = e.get_state()
+            assert rel_err(g, st.arr("gamma")) <= TOL and rel_err(lam, st.arr("lambda_")) <= TOL, (it, r)
+            assert np.array_equal(e.get_converged()[0], st.arr("converged")), (it, r)
+            nb, ne = int(bounds[r]), int(bounds[r + 1])
+            mem[nb:ne] = e.membership()[nb:ne]
+        if wc:
+            assert np.array_equal(mem, st.arr("member")), it
+    for e in engines:
+        e.close()
+    st.free()
