@@ -166,7 +166,8 @@ int svi_ls_mg_step(svi_ls *h, uint32_t iter, int annealing, int write_comm);
 /* also push the refreshed gamma rows, so that every shard holds the whole gamma (svi_ls_heldout on any pair,
  * svi_ls_get_state of the whole matrix) */
 int svi_ls_mg_share_gamma(svi_ls *h, int on);
-/* Without replication: svi_ls_heldout reads the rows of other shards straight from their arenas (peer loads), and
+/* Without replication: svi_ls_heldout (any pairs, on any shard, between two svi_ls_mg_step calls of ALL shards) reads
+ * the rows of other shards straight from their arenas (peer loads), and
  * the whole gamma is assembled on demand -- every shard calls svi_ls_mg_publish_gamma (pushes its rows to all
  * peers, asynchronous), after which svi_ls_get_state on any shard returns the whole matrix. */
 int svi_ls_mg_publish_gamma(svi_ls *h);
@@ -180,7 +181,9 @@ int svi_ls_mg_error(svi_ls *h);
  *   [7] wait for the own pushes to drain                  (exposed exchange)
  *   [8] side stream: first mphi push .. mphi flag raised  [9] side stream: first exp(Elogpi) push .. flag raised */
 int svi_ls_mg_timing(svi_ls *h, int enable, double *phase_ms, uint32_t *steps);
-/* membership words of the rows [first, first+count) only (a shard's own block) */
+/* membership words of the rows [first, first+count) only.  After svi_ls_mg_step a shard holds the complete words of
+ * its OWN block (the bits other shards set for its nodes are merged in after the sweep); svi_ls_get_membership on a
+ * shard returns its local replica, which is complete for those rows only. */
 int svi_ls_get_membership_rows(svi_ls *h, uint32_t first, uint32_t count, uint32_t *bits);
 
 typedef enum svi_buffer {
