@@ -232,7 +232,20 @@ void LinkSampling::create_device() {
   for (uint32_t i = 0; i < g; ++i) {
     DEV(svi_ls_peer_attach_local(devs_[i], g, i, bounds_.data(), devs_.data(), 0));
   }
-  for (uint32_t i = 0; i < g; ++i) DEV(svi_ls_set_state(devs_[i], gamma_.data(), lambda_.data()));
+  // every shard takes the whole start state (it derives the expectations of all rows itself): uploaded concurrently
+  std::fill(rc.begin(), rc.end(), 0);
+  th.clear();
+  for (uint32_t i = 0; i < g; ++i)
+    th.emplace_back([&, i] {
+      rc[i] = svi_ls_set_state(devs_[i], gamma_.data(), lambda_.data());
+      if (rc[i]) msg[i] = svi_ls_last_error();
+    });
+  for (auto &t : th) t.join();
+  for (uint32_t i = 0; i < g; ++i)
+    if (rc[i]) {
+      fprintf(stderr, "svinet: svi_ls_set_state on GPU %u failed: %s\n", i, msg[i].c_str());
+      exit(-1);
+    }
 }
 
 void LinkSampling::device_step(bool write_comm) {

@@ -177,6 +177,35 @@ def test_reference_host_code_over_the_library(cli, case):
             assert open(os.path.join(out, fname)).read() == golden_text(case, fname), fname
 
 
+def test_cli_load_validation_with_repeated_pairs(cli):
+    """-load-validation <file>: the reference keeps the held-out pairs in a std::map, so a file that repeats a pair
+    counts it once.  Both binaries run on the same file (the reference's own validation-edges.txt with a
+    few pairs repeated); validation.txt and the model must agree."""
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "svinet_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/svinet_ref not built (needs /root/reference at build time)")
+    ent = MANIFEST["c1_m30"]
+    pairs = [ln.split("\t")[:2] for ln in golden_text("c1_m30", "validation-edges.txt").strip().split("\n")]
+    with Scratch() as d:
+        inp = input_path(ent["input"], d)
+        text = "".join("%s\t%s\n" % (a, b) for a, b in pairs + pairs[:5] + pairs[3:4])
+        outs = {}
+        for tag, exe in (("ref", ref), ("ours", cli)):
+            w = os.path.join(d, tag)
+            os.makedirs(w)
+            os.symlink(inp, os.path.join(w, ent["input"]))
+            open(os.path.join(w, "held.txt"), "w").write(text)
+            p = subprocess.run([exe, "-file", ent["input"], "-n", "75", "-k", "4", "-link-sampling", "-max-iterations", "12",
+                                "-no-stop", "-load-validation", "held.txt"], cwd=w, stdout=subprocess.DEVNULL,
+                               stderr=subprocess.PIPE, timeout=600)
+            assert p.returncode == 0, p.stderr.decode()[-400:]
+            outs[tag] = os.path.join(w, ent["outdir"])
+        for fname in ("validation.txt", "gamma.txt", "lambda.txt"):
+            compare_numeric_text(open(os.path.join(outs["ours"], fname)).read(), open(os.path.join(outs["ref"], fname)).read(),
+                                 skip_cols=(1,) if fname == "validation.txt" else ())
+        assert open(os.path.join(outs["ours"], "communities.txt")).read() == open(os.path.join(outs["ref"], "communities.txt")).read()
+
+
 FA2_CASES = [c for c in MANIFEST if MANIFEST[c].get("mode") == "-rnode -stratified"]
 
 
