@@ -5,6 +5,7 @@
 #include "textio.hh"
 #include "pool.hh"
 #include "nmi.hh"
+#include "mt_jump.hh"
 
 #include <algorithm>
 #include <cassert>
@@ -431,10 +432,9 @@ void LinkSampling::init_gamma2() {
   const size_t chunk = std::max<size_t>(256, std::min<size_t>(1u << 14, (size_t)(1u << 22) / std::max(1u, k)));
   const unsigned nt = std::max(1u, std::min(16u, std::min<unsigned>(std::thread::hardware_concurrency(),
                                                                     (unsigned)(nl / 4096 + 1))));
-  std::vector<double> buf[2] = {std::vector<double>(chunk * k), std::vector<double>(chunk * k)};
   Pool pool(nt);
-  auto work = [&](double *u, size_t l0, size_t cnt) {
-    pool.run([&](unsigned t) {                       // phase A
+  auto work = [&](double *u, size_t l0, size_t cnt, bool normalise) {
+    if (normalise) pool.run([&](unsigned t) {        // phase A
       for (size_t i = cnt * t / nt; i < cnt * (t + 1) / nt; ++i) {
         double *phi = u + i * k;
         double s = .0;
@@ -452,39 +452,92 @@ void LinkSampling::init_gamma2() {
       }
     });
   };
-  // double-buffered: one producer thread fills chunk i+1 with the generator while the pool consumes chunk i
+  const size_t nchunks = (nl + chunk - 1) / chunk;
+  const size_t cw = chunk * k;                        // words (uniforms) per full chunk
+  // ---- many producers: disjoint pieces of the ONE mt19937 stream, reached by jump-ahead (mt_jump.hh) ----
+  // Producer t makes chunks t, t+T, t+2T, ...; chunk c starts c*cw words into the stream.  The first chunk comes from
+  // rng_ itself (it may sit in the middle of a block); the start state of every later chunk is a 624-word history
+  // window, moved on by t^(cw) or t^(T*cw) mod phi.  The appliers still see the chunks in order, so every row sees
+  // its additions in link order -- the result is bit-identical to the serial loop.
+  const char *fp = getenv("SVINET_INIT_PRODUCERS");
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  unsigned T = fp ? (unsigned)std::max(1, atoi(fp)) : std::max(1u, std::min(8u, hw / 2));
+  if (!fp && (double)nl * k < 4e8) T = 1;            // below ~0.5 s of generation the set-up does not pay
+  if (nchunks < 2 * (size_t)T || cw < 2 * 624 || !mtjump::ready()) T = 1;
+  const size_t R = 2 * (size_t)T;                    // ring of chunk buffers
+  std::vector<std::vector<double>> ring(R, std::vector<double>(cw));
   std::mutex m;
   std::condition_variable cv;
-  size_t produced = 0, consumed = 0;       // chunks
-  const size_t nchunks = (nl + chunk - 1) / chunk;
-  std::thread producer([&] {
-    for (size_t c = 0; c < nchunks; ++c) {
+  std::vector<size_t> ready(R, (size_t)-1);          // ready[b] = chunk held by buffer b
+  size_t consumed = 0;                                // chunks applied so far
+  Mt19937 last_state = rng_;
+  std::vector<std::vector<uint32_t>> start(T, std::vector<uint32_t>(624));
+  mtjump::Poly g_skip;
+  Mt19937 first = rng_;                               // producer 0 generates chunk 0 from the live generator
+  if (T > 1) {
+    Mt19937 probe = rng_;
+    const size_t r = probe.remaining_in_block();      // words before the next block boundary (< 624 <= cw)
+    std::vector<double> scratch(r + 1);
+    probe.uniform_fill(scratch.data(), r);            // now at a boundary: its array is the history window H0
+    uint32_t h[624];
+    probe.history(h);
+    mtjump::Poly g_first, g_chunk;
+    std::thread a([&] { g_first = mtjump::power_of_t(cw - r); });
+    std::thread b([&] { g_chunk = mtjump::power_of_t(cw); });
+    g_skip = mtjump::power_of_t((uint64_t)T * cw);
+    a.join();
+    b.join();
+    mtjump::apply(g_first, h);                        // history at the start of chunk 1
+    for (unsigned t = 1; t < T; ++t) {
+      std::copy(h, h + 624, start[t].begin());
+      mtjump::apply(g_chunk, h);                      // ... of chunk t+1
+    }
+    std::copy(h, h + 624, start[0].begin());          // chunk T: producer 0's second chunk
+  }
+  auto produce = [&](unsigned t) {
+    Mt19937 gen = first;
+    for (size_t c = t; c < nchunks; c += T) {
       {
         std::unique_lock<std::mutex> g(m);
-        cv.wait(g, [&] { return c < consumed + 2; });     // at most two chunks ahead of the consumer
+        cv.wait(g, [&] { return c < consumed + R; }); // buffer c % R is free once chunk c - R has been applied
       }
+      if (!(T == 1 || (t == 0 && c == 0))) gen.set_history(start[t].data());
       const size_t cnt = std::min(chunk, nl - c * chunk);
-      rng_.uniform_fill(buf[c & 1].data(), cnt * k);
+      double *u = ring[c % R].data();
+      gen.uniform_fill(u, cnt * k);
+      if (c == nchunks - 1) last_state = gen;         // the stream position after init_gamma2, as in the serial loop
+      if (T > 1) {
+        for (size_t i = 0; i < cnt; ++i) {            // phase A here: the producers are parallel, the pool only applies
+          double *phi = u + i * k;
+          double sum = .0;
+          for (uint32_t cc = 0; cc < k; ++cc) sum += phi[cc];
+          for (uint32_t cc = 0; cc < k; ++cc) phi[cc] = phi[cc] / sum;
+        }
+        if (c + T < nchunks && !(t == 0 && c == 0)) mtjump::apply(g_skip, start[t].data());
+      }
       {
         std::lock_guard<std::mutex> g(m);
-        produced = c + 1;
+        ready[c % R] = c;
       }
       cv.notify_all();
     }
-  });
+  };
+  std::vector<std::thread> producers;
+  for (unsigned t = 0; t < T; ++t) producers.emplace_back(produce, t);
   for (size_t c = 0; c < nchunks; ++c) {
     {
       std::unique_lock<std::mutex> g(m);
-      cv.wait(g, [&] { return produced > c; });
+      cv.wait(g, [&] { return ready[c % R] == c; });
     }
-    work(buf[c & 1].data(), c * chunk, std::min(chunk, nl - c * chunk));
+    work(ring[c % R].data(), c * chunk, std::min(chunk, nl - c * chunk), T == 1);
     {
       std::lock_guard<std::mutex> g(m);
       consumed = c + 1;
     }
     cv.notify_all();
   }
-  producer.join();
+  for (auto &p : producers) p.join();
+  rng_ = last_state;
 }
 
 int LinkSampling::load_model() {

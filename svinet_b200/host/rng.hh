@@ -53,6 +53,13 @@ class Mt19937 {
       i += take;
     }
   }
+  // ---- hooks for mt_jump.hh (several producers generating disjoint pieces of this one stream) ----
+  size_t remaining_in_block() const { return (size_t)(N - at_); }   // words left before the next refill
+  // the last 624 words produced, oldest first: only meaningful when remaining_in_block() == 0
+  void history(uint32_t out[624]) const { std::copy(x_, x_ + N, out); }
+  // continue from a history window: the next uniform() is the word that follows it
+  void set_history(const uint32_t in[624]) { std::copy(in, in + N, x_); at_ = N; }
+
   unsigned long uniform_int(unsigned long n) {
     const unsigned long scale = 0xffffffffUL / n;
     unsigned long k;
