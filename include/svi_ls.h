@@ -129,8 +129,10 @@ int svi_ls_phase_s3(svi_ls *h);
 int svi_ls_phase_finish(svi_ls *h, int annealing);
 /* phase_finish in two halves, for drivers that hide an exchange behind the s3 sweep:
  *   phase_refresh : gamma rescale, Elogpi, prune for the shard's rows.  Needs only `sum` of SVI_BUF_KVEC, so it
- *                   may run right after phase_node's all-reduce, BEFORE phase_s3; the s3 sweep then reads a
- *                   snapshot of `converged` taken here (the reference's s3 loop, :731-746, precedes prune, :761).
+ *                   may run right after phase_node's all-reduce, BEFORE phase_s3: `converged` is double-buffered,
+ *                   prune writes the copy the NEXT iteration reads and the s3 sweep still sees this iteration's
+ *                   flags (the reference's s3 loop, :731-746, precedes prune, :761).  SVI_BUF_CONVERGED names the
+ *                   freshly pruned copy from here on (ask for the pointer again after every refresh).
  *                   -> SVI_BUF_EXPPI rows, SVI_BUF_CONVERGED  [all-gather both, may overlap phase_s3]
  *   phase_lambda  : lambda, Elogbeta (needs s3); ends the iteration.
  * Order: phase_phi; phase_node; phase_refresh; phase_s3; phase_lambda  ==  phase_phi; phase_node; phase_s3;
