@@ -157,7 +157,10 @@ int svi_ls_phase_lambda(svi_ls *h, int annealing);
  *   one process, N GPUs : svi_ls_peer_attach_local with the N handles (the C++ CLI's -gpus N)
  *   bounds : [world+1] node blocks of all shards (bounds[rank] .. bounds[rank+1] is this handle's)
  *   chunks : pipeline chunks of the shard's block (0 = default 4); the mphi rows of a finished chunk travel beside
- *            the next chunk's sweep */
+ *            the next chunk's sweep
+ * A shard works on four streams of its own (sweeps, owned-segment sweeps, node passes, pushes) and parks flag-wait
+ * kernels at their heads: a process that hosts shards should start CUDA with CUDA_DEVICE_MAX_CONNECTIONS >= 16 (32
+ * when several shards share one device) so that these streams never share a hardware queue. */
 size_t svi_ls_peer_blob_bytes(void);
 int svi_ls_peer_export(svi_ls *h, void *blob, size_t blob_bytes);
 int svi_ls_peer_attach(svi_ls *h, uint32_t world, uint32_t rank, const uint32_t *bounds, const void *blobs,

@@ -24,6 +24,9 @@ static void term_handler(int sig) {
 
 int main(int argc, char **argv) {
   signal(SIGTERM, term_handler);
+  // -gpus N: a shard runs four streams with flag-wait kernels at their heads; give CUDA enough hardware queues that
+  // no two of them alias (read when CUDA initialises; a value set by the user is kept)
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   if (argc == 1) {
     Env::usage();
     exit(-1);
