@@ -212,7 +212,8 @@ def verify_sampled_rows(step_once, get_state, get_converged, n, k, links, alpha,
 def run_ours(args):
     # a shard runs four streams of its own beside torch's, with flag-wait kernels at their heads: enough hardware queues
     # that no two of them alias (include/svi_ls.h, svi_ls_mg_step).  Read when CUDA initialises.
-    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import torch
     import torch.distributed as dist
     from svinet_b200 import synth
