@@ -144,6 +144,24 @@ def test_init_communities_startup_state(cli):
         g.close()
 
 
+def test_nmi_ground_truth_files_equal_the_references(cli):
+    """-nmi <file>: Network::load_ground_truth + write_gt_communities (network.cc:254-307, 508-536) -- ground_truth.txt
+    and ground_truth_community_sizes.txt as the reference wrote them for the LFR example (tests/golden/lfr_nmi/, from
+    `svinet_ref ... -nmi LFR-ground-truth-n1000-k28.txt`)."""
+    ent = MANIFEST["lfr_k28_m20"]
+    with Scratch() as d:
+        for name in (ent["input"], "LFR-ground-truth-n1000-k28.txt"):
+            inp, local = input_path(name, d), os.path.join(d, name)
+            if not os.path.exists(local):
+                os.symlink(inp, local)
+        dump = os.path.join(d, "dump"); os.makedirs(dump)
+        subprocess.check_call([cli, "-file", ent["input"], "-n", "1000", "-k", "28", "-link-sampling", "-nmi",
+                               "LFR-ground-truth-n1000-k28.txt", "-dump-init", dump], cwd=d, stdout=subprocess.DEVNULL)
+        out = os.path.join(d, ent["outdir"])
+        for f in ("ground_truth.txt", "ground_truth_community_sizes.txt"):
+            assert open(os.path.join(out, f)).read() == golden_text("lfr_nmi", f), f
+
+
 def test_cli_refuses_other_engines(cli):
     with Scratch() as d:
         p = subprocess.run([cli, "-file", "x", "-n", "5", "-k", "2", "-batch"], cwd=d, capture_output=True)
