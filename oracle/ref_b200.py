@@ -3,8 +3,8 @@
 
 TEST INFRASTRUCTURE.  Reads the reference sources where they lie (/root/reference/src, never copied into the
 repository), writes PATCHED COPIES of linksampling.{hh,cc} plus symlinks to the other, unmodified files into
-oracle/_ref/b200_src/ (git-ignored build output), where `make -C oracle ref_b200` compiles them against
-include/svi_ls.h and links svinet_b200/lib/libsvi_ls.so -> oracle/_ref/svinet_ref_b200.
+oracle/_ref/b200_src/ (a build intermediate: `make -C oracle ref_b200` compiles it against include/svi_ls.h, links
+svinet_b200/lib/libsvi_ls.so -> oracle/_ref/svinet_ref_b200, and removes the directory again).
 
 The edits are anchored on identifiers (regular expressions), not on a diff, and are exactly INTEGRATION.md B.1-B.4:
   B.1  linksampling.hh   #include "svi_ls.h", one member + four private helpers
