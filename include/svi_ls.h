@@ -32,7 +32,7 @@ typedef enum svi_status {
   SVI_ERR_INVALID = -1,   /* bad argument                                   */
   SVI_ERR_CUDA = -2,      /* a CUDA runtime call or kernel failed           */
   SVI_ERR_NOMEM = -3,     /* host or device allocation failed               */
-  SVI_ERR_UNSUPPORTED = -4/* e.g. K larger than the register-tiled kernels  */
+  SVI_ERR_UNSUPPORTED = -4/* e.g. K > 65535 (the reference's uint16_t ids)   */
 } svi_status;
 
 typedef struct svi_ls svi_ls; /* opaque */

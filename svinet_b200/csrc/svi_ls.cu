@@ -7,6 +7,7 @@
 #include "svi_common.h"
 #include "svi_ls_kernels.cuh"
 #include "svi_ls_ring.cuh"
+#include "svi_ls_wide.cuh"
 #include "svi_ls_build.cuh"
 #include "svi_ls_mg.cuh"
 
@@ -147,6 +148,67 @@ struct Tile {
   }
   static Ops ops() {
     Ops o{phi, node, s3, lambda, refresh, heldout, max_blocks_node, max_blocks_s3, G, V, L ? 1 : 0};
+    o.preload = preload;
+    return o;
+  }
+};
+
+// K > 1024: one block per work item, columns strided over its threads (svi_ls_wide.cuh); always the log domain
+struct WideTile {
+  static constexpr int T = (int)svi::kWideT;
+  static void phi(const Params &P, cudaStream_t st, bool sparse, bool comm, uint32_t s0, uint32_t s1, uint32_t t0,
+                  uint32_t t1, uint32_t pub) {
+    const uint64_t cnt = (uint64_t)(s1 - s0) + (t1 - t0);
+    if (!cnt) return;
+    const uint32_t blocks = (uint32_t)cnt;   // (a segment owns a K-row of `part`: 2^31 of them do not fit any device)
+    if (sparse && comm) svi::k_phi_wide<true, true><<<blocks, T, 0, st>>>(P, s0, s1, t0, t1, pub);
+    else if (sparse) svi::k_phi_wide<true, false><<<blocks, T, 0, st>>>(P, s0, s1, t0, t1, pub);
+    else if (comm) svi::k_phi_wide<false, true><<<blocks, T, 0, st>>>(P, s0, s1, t0, t1, pub);
+    else svi::k_phi_wide<false, false><<<blocks, T, 0, st>>>(P, s0, s1, t0, t1, pub);
+  }
+  static void node(const Params &P, cudaStream_t st, uint32_t blocks) {
+    svi::k_node_wide<<<blocks, T, 0, st>>>(P, svi::wide_cap(P.ld));
+  }
+  static void s3(const Params &P, cudaStream_t st, uint32_t blocks) {
+    svi::k_s3_wide<<<blocks, T, 0, st>>>(P, svi::wide_cap(P.ld));
+  }
+  static void lambda(const Params &P, cudaStream_t st, int annealing, int update) {
+    svi::k_lambda<true><<<1, kThreads, 0, st>>>(P, annealing, update);
+  }
+  static void refresh(const Params &P, cudaStream_t st, bool from_gacc) {
+    const uint32_t rows = P.node_end - P.node_begin;
+    if (!rows) return;
+    if (from_gacc) svi::k_refresh_wide<true><<<rows, T, 0, st>>>(P);
+    else svi::k_refresh_wide<false><<<rows, T, 0, st>>>(P);
+  }
+  static void heldout(const Params &P, cudaStream_t st, uint64_t np, const uint32_t *p, const uint32_t *q,
+                      const uint8_t *y, double eps, double *out, unsigned long long *bad, const svi::Peers *peer_rows) {
+    if (!np) return;
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(np, 1u << 20);   // grid-stride over the pairs
+    if (peer_rows) svi::k_heldout_wide<svi::Peers><<<blocks, T, 0, st>>>(P, *peer_rows, np, p, q, y, eps, out, bad);
+    else svi::k_heldout_wide<svi::LocalRows><<<blocks, T, 0, st>>>(P, svi::LocalRows{P.gamma}, np, p, q, y, eps, out, bad);
+  }
+  // persistent grids: a block keeps a [3][cap] (node pass) or [cap] (s3 sweep) slot of column partials in global
+  // memory, so the grid is kept small -- 2 / 8 blocks per SM (K = 65 535: 3.7 GB of partials)
+  static int max_blocks_node(int sms) { return 2 * sms; }
+  static int max_blocks_s3(int sms) { return 8 * sms; }
+  static void preload() {
+    touch(svi::k_phi_wide<false, false>);
+    touch(svi::k_phi_wide<false, true>);
+    touch(svi::k_phi_wide<true, false>);
+    touch(svi::k_phi_wide<true, true>);
+    touch(svi::k_node_wide);
+    touch(svi::k_s3_wide);
+    touch(svi::k_lambda<true>);
+    touch(svi::k_refresh_wide<true>);
+    touch(svi::k_refresh_wide<false>);
+    touch(svi::k_heldout_wide<svi::LocalRows>);
+    touch(svi::k_heldout_wide<svi::Peers>);
+  }
+  static Ops ops(uint32_t k) {
+    const uint32_t ld = (k + 3u) & ~3u;
+    // lanes * vec * 2 = the slot width k_reduce_kpart is told (svi::wide_cap)
+    Ops o{phi, node, s3, lambda, refresh, heldout, max_blocks_node, max_blocks_s3, T, (int)(svi::wide_cap(ld) / (2u * T)), 1};
     o.preload = preload;
     return o;
   }
@@ -294,6 +356,7 @@ bool pick_ops(uint32_t k, Ops *o) {
   else if (k <= 512) *o = Tile<32, 8, true>::ops();
   else if (k <= 768) *o = Tile<32, 12, true>::ops();
   else if (k <= 1024) *o = Tile<32, 16, true>::ops();
+  else if (k <= 65535) *o = WideTile::ops(k);   // the reference's limit: communities are uint16_t (src/env.hh:37)
   else return false;
   pick_ring(k, o);
   return true;
@@ -496,7 +559,7 @@ int svi_ls_create(const svi_ls_config *cfg, const uint32_t *links, const double 
   if (cfg->node_begin > cfg->node_end || cfg->node_end > cfg->n)
     return fail(SVI_ERR_INVALID, "svi_ls_create: bad shard [%u,%u) for n=%u", cfg->node_begin, cfg->node_end, cfg->n);
   Ops ops;
-  if (!pick_ops(cfg->k, &ops)) return fail(SVI_ERR_UNSUPPORTED, "svi_ls_create: k=%u not supported (max 1024)", cfg->k);
+  if (!pick_ops(cfg->k, &ops)) return fail(SVI_ERR_UNSUPPORTED, "svi_ls_create: k=%u not supported (max 65535)", cfg->k);
 
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));

@@ -82,7 +82,7 @@ def test_invalid_arguments_are_rejected(lib):
     cfg = engine.SviConfig(n=10, k=4, nlinks=0, alpha=0.25, eta0=1, eta1=1, ones=0, device=-1, seg_len=0,
                            node_begin=5, node_end=11)
     assert lib.svi_ls_create(C.byref(cfg), None, None, C.byref(h)) == -1
-    cfg = engine.SviConfig(n=10, k=5000, nlinks=0, alpha=0.25, eta0=1, eta1=1, ones=0, device=-1, seg_len=0,
+    cfg = engine.SviConfig(n=10, k=70000, nlinks=0, alpha=0.25, eta0=1, eta1=1, ones=0, device=-1, seg_len=0,
                            node_begin=0, node_end=10)
     assert lib.svi_ls_create(C.byref(cfg), None, None, C.byref(h)) == -4
     assert lib.svi_ls_step(None, 0, 1, 0) == -1
