@@ -156,6 +156,7 @@ struct Tile {
 // K > 1024: one block per work item, columns strided over its threads (svi_ls_wide.cuh); always the log domain
 struct WideTile {
   static constexpr int T = (int)svi::kWideT;
+  static_assert(T == kThreads, "svi_ls_create sizes the persistent grids of a tile from kThreads / Ops::lanes");
   static void phi(const Params &P, cudaStream_t st, bool sparse, bool comm, uint32_t s0, uint32_t s1, uint32_t t0,
                   uint32_t t1, uint32_t pub) {
     const uint64_t cnt = (uint64_t)(s1 - s0) + (t1 - t0);

@@ -76,6 +76,32 @@ def test_active_set_branch_and_newly_converged_nodes():
     eng.close(); st.free()
 
 
+def test_empty_link_list_single_link_and_determinism():
+    for n, links in [(3, np.zeros((0, 2), dtype=np.uint32)), (2, np.array([[0, 1]], dtype=np.uint32))]:
+        k = 1030
+        st = make_state(n, k, links, seed=1)
+        st.c.ones = max(1, links.shape[0])
+        st.arr("gamma")[:] = 1.0 / k + np.arange(n * k).reshape(n, k) / 7.0
+        st.refresh_expectations()
+        eng = engine_from_state(st, max(1, links.shape[0]))
+        st.step(0, 0, 1); eng.step(0, 0, 1)
+        compare_sweep(eng, st, "n=%d" % n, check_member=True)
+        eng.close(); st.free()
+    # no floating-point atomics: two handles end bit-identical
+    n, k = 100, 1200
+    links = random_links(n, 500, np.random.default_rng(4), hub=True)
+    st = make_state(n, k, links, seed=9)
+    outs = []
+    for _ in range(2):
+        eng = engine_from_state(st, links.shape[0])
+        for it in range(3):
+            eng.step(it, it < 2, 1)
+        outs.append(eng.get_state() + (eng.membership_bits(),))
+        eng.close()
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+    st.free()
+
+
 def test_heldout_matches_the_literal_double_sum():
     n, k = 30, 1027
     rng = np.random.default_rng(8)

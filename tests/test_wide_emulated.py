@@ -130,6 +130,19 @@ def test_active_set_branch_and_newly_converged_nodes():
     eng.close(); st.free()
 
 
+def test_empty_link_list_and_a_single_link():
+    for n, links in [(3, np.zeros((0, 2), dtype=np.uint32)), (2, np.array([[0, 1]], dtype=np.uint32))]:
+        k = 1030
+        st = make_state(n, k, links, seed=1)
+        st.c.ones = max(1, links.shape[0])
+        st.arr("gamma")[:] = 1.0 / k + np.arange(n * k).reshape(n, k) / 7.0
+        st.refresh_expectations()
+        eng = engine_for(st, links, FAST_T)
+        st.step(0, 0, 1); eng.step(0, 0, 1)
+        compare_sweep(eng, st, "n=%d" % n, check_member=True)
+        eng.close(); st.free()
+
+
 def test_heldout_matches_the_literal_double_sum():
     n, k = 12, 1027
     rng = np.random.default_rng(8)
