@@ -4,6 +4,7 @@
 #include "../../include/svi_fa2.h"
 #include "svi_common.h"
 #include "svi_fa2_kernels.cuh"
+#include "svi_fa2_wide.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -26,6 +27,8 @@ struct Fa2Ops {
   void (*one_pair)(const Fa2Params &, cudaStream_t, uint32_t, uint32_t, int, double *, uint32_t *);
   int (*pair_blocks)(int sms);
   int lanes, vec, cap;
+  int groups_per_block;      // pairs a block of the pair kernel works on at a time (k_fa2_lambda: which blocks had pairs)
+  int wide_rows;             // K > 512: scratch rows (of ld doubles) per pair block, else 0
 };
 
 template <int G, int V>
@@ -61,7 +64,36 @@ struct Fa2Tile {
       per_sm = 1;
     return per_sm * sms;
   }
-  static Fa2Ops ops() { return Fa2Ops{prep, pairs, blend, heldout, one_pair, pair_blocks, G, V, CAP}; }
+  static Fa2Ops ops() { return Fa2Ops{prep, pairs, blend, heldout, one_pair, pair_blocks, G, V, CAP, T / G, 0}; }
+};
+
+// K > 512: one block per pair / row, columns strided over its threads (svi_fa2_wide.cuh).  The slot width of the block
+// partials depends on K, so these launchers read it from the handle's parameters.
+struct Fa2WideTile {
+  static constexpr int T = (int)svi::kWideT;
+  static uint32_t cap_of(const Fa2Params &P) { return svi::wide_cap(P.ld); }
+  static void prep(const Fa2Params &P, cudaStream_t st) { svi::k_fa2_prep_wide<<<1, T, 0, st>>>(P); }
+  static void pairs(const Fa2Params &P, cudaStream_t st) { svi::k_fa2_pairs_wide<<<P.pair_blocks, T, 0, st>>>(P, cap_of(P)); }
+  static void blend(const Fa2Params &P, cudaStream_t st) {
+    svi::k_fa2_blend_wide<<<std::max<uint32_t>(1, std::min<uint32_t>(P.n, 148u * 8)), T, 0, st>>>(P, cap_of(P));
+  }
+  static void heldout(const Fa2Params &P, cudaStream_t st, uint64_t np, const uint32_t *p, const uint32_t *q,
+                      const uint8_t *y, double *out) {
+    if (!np) return;
+    svi::k_fa2_heldout_wide<<<(uint32_t)std::min<uint64_t>(np, 1u << 20), T, 0, st>>>(P, np, p, q, y, out);
+  }
+  static void one_pair(const Fa2Params &P, cudaStream_t st, uint32_t p, uint32_t q, int y, double *phi,
+                       uint32_t *rounds) {
+    // its six scratch rows follow the pair blocks' (svi_fa2_create)
+    double *rows = P.wide + (size_t)P.pair_blocks * svi::kFa2WideRows * P.ld;
+    svi::k_fa2_one_pair_wide<<<1, T, 0, st>>>(P, rows, p, q, y, phi, rounds);
+  }
+  static int pair_blocks(int sms) { return 2 * sms; }   // (each block keeps 5 K-rows of scratch + 2 partial rows)
+  static Fa2Ops ops(uint32_t k) {
+    const uint32_t ld = (k + 3u) & ~3u, cap = svi::wide_cap(ld);
+    return Fa2Ops{prep, pairs, blend, heldout, one_pair, pair_blocks, T, (int)(cap / (2u * T)), (int)cap, 1,
+                  (int)svi::kFa2WideRows};
+  }
 };
 
 bool pick_fa2(uint32_t k, Fa2Ops *o) {
@@ -76,6 +108,7 @@ bool pick_fa2(uint32_t k, Fa2Ops *o) {
   else if (k <= 256) *o = Fa2Tile<32, 4>::ops();
   else if (k <= 384) *o = Fa2Tile<32, 6>::ops();
   else if (k <= 512) *o = Fa2Tile<32, 8>::ops();
+  else if (k <= 65535) *o = Fa2WideTile::ops(k);   // the reference's limit: communities are uint16_t (src/env.hh:37)
   else return false;
   return true;
 }
@@ -107,7 +140,7 @@ struct svi_fa2 {
   bool have_graph = false;
   // owned device memory
   double *d_gamma = nullptr, *d_lambda = nullptr, *d_elogbeta = nullptr, *d_elogf = nullptr, *d_epi = nullptr;
-  double *d_partS = nullptr, *d_partL = nullptr, *d_stage = nullptr;
+  double *d_partS = nullptr, *d_partL = nullptr, *d_stage = nullptr, *d_wide = nullptr;
   uint32_t *d_pairs = nullptr, *d_shuffled = nullptr, *d_adj = nullptr;
   uint64_t *d_adj_off = nullptr, *d_heldout = nullptr;
   uint8_t *d_touched = nullptr;
@@ -176,7 +209,7 @@ void launch_iteration(svi_fa2 *h, uint64_t nodec) {
   h->ops.prep(h->P, h->stream);
   h->ops.pairs(h->P, h->stream);
   if (!h->P.lazy) h->ops.blend(h->P, h->stream);
-  svi::k_fa2_lambda<<<1, 256, 0, h->stream>>>(h->P, (uint32_t)h->ops.cap, 128u / (uint32_t)h->ops.lanes);
+  svi::k_fa2_lambda<<<1, 256, 0, h->stream>>>(h->P, (uint32_t)h->ops.cap, (uint32_t)h->ops.groups_per_block);
   if (h->P.lazy) {
     // c shrinks by (1 - rho) per iteration: exp(-2 sqrt(T)) in the long run.  Re-base the stored rows long
     // before c*u leaves the FP64 range (every ~2e4 iterations at the default step sizes).
@@ -211,7 +244,7 @@ int svi_fa2_create(const svi_fa2_config *cfg, svi_fa2 **out) {
   if (cfg->n < 2 || cfg->k == 0) return fail(SVI_ERR_INVALID, "svi_fa2_create: need n >= 2 and k >= 1");
   if (!(cfg->epsilon > 0.0) || cfg->m_sets == 0) return fail(SVI_ERR_INVALID, "svi_fa2_create: bad epsilon / m_sets");
   Fa2Ops ops;
-  if (!pick_fa2(cfg->k, &ops)) return fail(SVI_ERR_UNSUPPORTED, "svi_fa2_create: k=%u not supported (max 512)", cfg->k);
+  if (!pick_fa2(cfg->k, &ops)) return fail(SVI_ERR_UNSUPPORTED, "svi_fa2_create: k=%u not supported (max 65535)", cfg->k);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(SVI_ERR_CUDA, "svi_fa2_create: no CUDA device");
   int dev = cfg->device;
@@ -249,6 +282,8 @@ int svi_fa2_create(const svi_fa2_config *cfg, svi_fa2 **out) {
   A(dalloc(h, &h->d_epi, P.ld));
   A(dalloc(h, &h->d_partS, (size_t)P.pair_blocks * ops.cap));
   A(dalloc(h, &h->d_partL, (size_t)P.pair_blocks * ops.cap));
+  if (ops.wide_rows)
+    A(dalloc(h, &h->d_wide, ((size_t)P.pair_blocks * ops.wide_rows + svi::kFa2WideOneRows) * P.ld));
   A(dalloc(h, &h->d_pairs, 2 * (size_t)P.cap_pairs));
   A(dalloc(h, &h->d_touched, P.n));
   A(dalloc(h, &h->d_ctrl, 1));
@@ -261,7 +296,7 @@ int svi_fa2_create(const svi_fa2_config *cfg, svi_fa2 **out) {
   }
   P.gamma = h->d_gamma; P.lambda = h->d_lambda; P.elogbeta = h->d_elogbeta; P.elogf = h->d_elogf;
   P.epi_start = h->d_epi; P.partS = h->d_partS; P.partL = h->d_partL; P.pairs = h->d_pairs;
-  P.touched = h->d_touched; P.ctrl = h->d_ctrl;
+  P.touched = h->d_touched; P.ctrl = h->d_ctrl; P.wide = h->d_wide;
   *out = h;
   return SVI_OK;
 }
@@ -270,7 +305,7 @@ void svi_fa2_destroy(svi_fa2 *h) {
   if (!h) return;
   DevGuard guard(h->device);
   cudaStreamSynchronize(h->stream);
-  void *ptrs[] = {h->d_gamma, h->d_lambda, h->d_elogbeta, h->d_elogf, h->d_epi, h->d_partS, h->d_partL, h->d_stage,
+  void *ptrs[] = {h->d_gamma, h->d_lambda, h->d_elogbeta, h->d_elogf, h->d_epi, h->d_partS, h->d_partL, h->d_stage, h->d_wide,
                   h->d_pairs, h->d_shuffled, h->d_adj, h->d_adj_off, h->d_heldout, h->d_touched, h->d_ctrl,
                   h->d_ballots, h->d_counts};
   for (void *p : ptrs)

@@ -55,6 +55,7 @@ struct Fa2Params {
   uint8_t *touched;         // [n]
   Fa2Ctrl *ctrl;
   double *partS, *partL;    // [pair_blocks * cap] block partials
+  double *wide;             // K > 512 (svi_fa2_wide.cuh): scratch rows of the pair blocks, else null
   uint32_t pair_blocks;
   // graph for device-side draws
   const uint64_t *adj_off;  // [n+1]

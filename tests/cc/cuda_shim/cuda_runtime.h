@@ -34,5 +34,14 @@ static inline unsigned long long atomicMax(unsigned long long *p, unsigned long 
   while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
   return old;
 }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
+  return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}
+// parse-only (draw / eager-blend kernels of the register tiles, never run in the emulation)
+template <class T> static inline T __ldcs(const T *p) { return *p; }
+template <class T> static inline void __stcs(T *p, T v) { *p = v; }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static inline unsigned __ballot_sync(unsigned, int) { std::abort(); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 using std::max;
 using std::min;

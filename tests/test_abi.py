@@ -50,7 +50,7 @@ def test_fa2_header_symbols_all_exported(lib):
     assert (cfg.n, cfg.k, cfg.alpha, cfg.tau0, cfg.m_sets, cfg.online_iterations) == (100, 8, 0.125, 1025.0, 10, 50)
     h = C.c_void_p()
     assert lib.svi_fa2_create(None, C.byref(h)) == -1
-    cfg.k = 5000
+    cfg.k = 70000
     assert lib.svi_fa2_create(C.byref(cfg), C.byref(h)) == -4
     assert lib.svi_fa2_step(None, 0, 0, 0, 0, None) == -1
 
