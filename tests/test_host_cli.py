@@ -305,3 +305,34 @@ def test_link_sampling_resume_from_saved_model_text(cli):
         open(os.path.join(saved, "gamma.txt"), "w").write("\n".join(gtxt.strip().split("\n")[:-5]) + "\n")
         p = subprocess.run(base + ["-load", "saved/", "-dump-init", dump], cwd=d, capture_output=True)
         assert p.returncode != 0 and b"rows" in p.stderr
+
+
+# ---- K beyond the register tiles (the device side: svi_ls_wide.cuh / svi_fa2_wide.cuh) --------------------------------
+def test_startup_state_at_large_k_both_modes(cli):
+    """The host side has no K limit of its own below the reference's 65 535: start-up state at K = 1500
+    (-link-sampling) and K = 700 (-rnode -stratified) bit-identical to the oracle's."""
+    from test_oracle_fa2_golden import fa2_opts
+    with Scratch() as d:
+        inp = input_path("assort-75-4.txt", d)
+        local = os.path.join(d, "assort-75-4.txt")
+        if not os.path.exists(local):
+            os.symlink(inp, local)
+        g = orc.Graph.read(inp, 75)
+        k = 1500
+        dump = os.path.join(d, "dump_ls"); os.makedirs(dump)
+        subprocess.check_call([cli, "-file", "assort-75-4.txt", "-n", "75", "-k", str(k), "-link-sampling", "-dump-init", dump],
+                              cwd=d, stdout=subprocess.DEVNULL)
+        m = orc.Model(g, k)
+        st = m.state
+        assert np.array_equal(np.fromfile(os.path.join(dump, "gamma.f64")).reshape(-1, k), st.arr("gamma"))
+        assert np.array_equal(np.fromfile(os.path.join(dump, "lambda.f64")).reshape(k, 2), st.arr("lambda_"))
+        assert np.array_equal(np.fromfile(os.path.join(dump, "links.u32"), dtype=np.uint32).reshape(-1, 2), st.arr("links"))
+        m.close()
+        k = 700
+        dump = os.path.join(d, "dump_fa2"); os.makedirs(dump)
+        subprocess.check_call([cli, "-file", "assort-75-4.txt", "-n", "75", "-k", str(k), "-rnode", "-stratified",
+                               "-dump-init", dump], cwd=d, stdout=subprocess.DEVNULL)
+        m2 = orc.Fa2Model(g, k, **fa2_opts([]))
+        assert np.array_equal(np.fromfile(os.path.join(dump, "gamma.f64")).reshape(-1, k), m2.gamma)
+        assert np.array_equal(np.fromfile(os.path.join(dump, "lambda.f64")).reshape(k, 2), m2.lambda_)
+        m2.close(); g.close()
