@@ -233,3 +233,38 @@ def test_two_and_three_shards_on_one_gpu():
     sched = [(0, 1, 0), (1, 1, 1), (2, 0, 1), (3, 0, 0)]
     assert sharded_vs_oracle(n, k, links, g0, conv, [0, 70, n], 3, sched, seg_len=16, share=False) > 0
     assert sharded_vs_oracle(n, k, links, g0, conv, [0, 50, 111, n], 1, sched, seg_len=16, share=True) > 0
+
+
+def test_cli_output_directory_at_k_1100():
+    """The drop-in CLI end to end with 1100 communities: `svinet -link-sampling -k 1100 -max-iterations 8` against the
+    files the oracle's writers produce for the same run (the oracle's writers are pinned to the reference's bytes on the
+    golden fixtures, tests/test_oracle_golden.py): numeric files within one unit of the last printed digit,
+    communities.txt byte for byte."""
+    import os
+    import subprocess
+    from golden_util import Scratch, compare_numeric_text, input_path
+    from svinet_b200 import build as svbuild
+    cli = svbuild.build_cli()
+    k = 1100
+    with Scratch() as d:
+        inp = input_path("assort-75-4.txt", d)
+        if not os.path.exists(os.path.join(d, "assort-75-4.txt")):
+            os.symlink(inp, os.path.join(d, "assort-75-4.txt"))
+        p = subprocess.run([cli, "-file", "assort-75-4.txt", "-n", "75", "-k", str(k), "-link-sampling", "-max-iterations", "8"],
+                           cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=600)
+        assert p.returncode == 0, p.stderr.decode()
+        out = os.path.join(d, "n75-k%d-mmsb-linksampling" % k)
+        g = orc.Graph.read(inp, 75)
+        m = orc.Model(g, k, max_iterations=8)
+        m.run()
+        want = os.path.join(d, "want")
+        m.write_outputs(want)
+        m.close(); g.close()
+        flips = {}
+        for fname in ("gamma.txt", "lambda.txt", "groups.txt", "validation.txt", "max.txt"):
+            flips[fname] = compare_numeric_text(open(os.path.join(out, fname)).read(), open(os.path.join(want, fname)).read(),
+                                                skip_cols=(1,) if fname in ("validation.txt", "max.txt") else ())
+        for fname in ("communities.txt", "validation-edges.txt"):
+            assert open(os.path.join(out, fname)).read() == open(os.path.join(want, fname)).read(), fname
+        nf, noff = flips["gamma.txt"]
+        assert noff <= max(2, nf // 1000), flips

@@ -61,3 +61,37 @@ def test_device_draws_lazy_equals_eager_and_is_deterministic():
     assert np.all(np.isfinite(gl)) and np.all(gl > 0)
     assert rel_err(gl, ge) <= 1e-9 and rel_err(ll, le) <= 1e-9
     assert np.array_equal(gl, g2) and np.array_equal(ll, l2)
+
+
+def test_cli_output_directory_at_k_700():
+    """`svinet -rnode -stratified -k 700 -max-iterations 120 -rfreq 40` against the files the FastAMM2 oracle's writers
+    produce for the same run (pinned to the reference's bytes on the golden fixtures, tests/test_oracle_fa2_golden.py)."""
+    import os
+    import subprocess
+    from golden_util import Scratch, compare_numeric_text, input_path
+    from svinet_b200 import build as svbuild
+    cli = svbuild.build_cli()
+    k = 700
+    with Scratch() as d:
+        inp = input_path("assort-75-4.txt", d)
+        if not os.path.exists(os.path.join(d, "assort-75-4.txt")):
+            os.symlink(inp, os.path.join(d, "assort-75-4.txt"))
+        p = subprocess.run([cli, "-file", "assort-75-4.txt", "-n", "75", "-k", str(k), "-rnode", "-stratified",
+                            "-max-iterations", "120", "-rfreq", "40"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE,
+                           timeout=600)
+        assert p.returncode == 0, p.stderr.decode()
+        out = os.path.join(d, "n75-k%d-mmsb-Srnode" % k)
+        g = orc.Graph.read(inp, 75)
+        m = orc.Fa2Model(g, k, max_iterations=120, reportfreq=40)
+        m.run()
+        want = os.path.join(d, "want")
+        m.write_outputs(want)
+        m.close(); g.close()
+        flips = {}
+        for fname in ("gamma.txt", "lambda.txt", "groups.txt", "heldout.txt"):
+            flips[fname] = compare_numeric_text(open(os.path.join(out, fname)).read(), open(os.path.join(want, fname)).read(),
+                                                skip_cols=(1,) if fname == "heldout.txt" else ())
+        for fname in ("communities.txt", "communities_size.txt", "summary.txt", "heldout-pairs.txt"):
+            assert open(os.path.join(out, fname)).read() == open(os.path.join(want, fname)).read(), fname
+        nf, noff = flips["gamma.txt"]
+        assert noff <= max(2, nf // 1000), flips
