@@ -42,6 +42,7 @@ WORKLOADS = {
     "c3": (100_000, 100, 5_000_000),
     "c2s": (17_903, 20, 196_972),          # AstroPh-shaped synthetic
     "tiny": (2_000, 20, 20_000),
+    "widek": (50_000, 2048, 1_000_000),    # K > 1024: the block-per-row kernels (svi_ls_wide.cuh); not a BASELINE config
 }
 METRIC = "link_sampling_edge_updates_per_sec"
 UNIT = "edge-updates/s"
